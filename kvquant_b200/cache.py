@@ -1,0 +1,396 @@
+"""KV-cache managers.
+
+* `QuantK` / `QuantV` mirror the reference's cache-manager classes
+  (deployment/transformers/src/transformers/models/llama/modeling_llama.py:352-975 and 978-1385): same constructor
+  arguments, attributes (kcache / lookup_table / outliers / outlier_indices / klen ...), methods and return values,
+  so the reference's LlamaAttention code drives them unchanged.  They call the legacy 34-op surface
+  (kvquant_b200.quant_cuda) and keep the reference's host-side top-K glue, but on the GPU (torch.topk on device
+  instead of a .cpu() round trip -- same result, no blocking D2H).
+* `LayerCache` is the native path: one fused device-side append (`kvq_append_kv_fused`) and one fused decode
+  attention (`kvq_attend`) per layer per token, no host synchronisation, CUDA-graph capturable.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import quant_cuda as qc
+
+HEAD_DIM = 128
+
+
+def n_outliers_each(hidden_size: int, sparsity_threshold: float) -> int:
+    """threshold_k of the reference (modeling_llama.py:707): 21 for hidden 4096 at 0.99."""
+    return int(((1 - sparsity_threshold) / 2) * hidden_size) + 1
+
+
+def build_k_lookup_table(upper, lower, centroids, num_heads, normscale=None, normoffset=None, device="cuda"):
+    """Per-channel K LUT exactly as QuantK.load_lookup_table builds it (modeling_llama.py:447-501): thresholds are
+    rounded through fp16, offset/range are computed in fp16, LUT = cent*range + offset in fp32 (two roundings).
+    Vectorised (the reference loops 4096 times in Python).  Returns dict of CUDA tensors."""
+    up16 = torch.as_tensor(np.asarray(upper, dtype=np.float32)).to(device).half().flatten()
+    lo16 = torch.as_tensor(np.asarray(lower, dtype=np.float32)).to(device).half().flatten()
+    cent = torch.as_tensor(np.asarray(centroids, dtype=np.float32)).to(device).flatten().sort().values
+    offset = (up16 + lo16) / 2
+    rangeval = (up16 - lo16) / 2
+    sf = rangeval.float()[:, None]
+    off = offset.float()[:, None]
+    lut = (cent[None, :] * sf + off).contiguous()
+    out = dict(lut=lut.view(num_heads, HEAD_DIM, -1), cent=cent, thr_upper=up16.float(), thr_lower=lo16.float(),
+               zeropoint=offset.float(), lut2=None)
+    if normscale is not None:
+        c2 = cent * float(normscale) + float(normoffset)
+        out["lut2"] = (c2[None, :] * sf + off).contiguous().view(num_heads, HEAD_DIM, -1)
+    return out
+
+
+class LayerCache:
+    """Native quantised K+V cache of one layer (reference-compatible tensor layouts)."""
+
+    def __init__(self, bits, num_heads, max_len, klut, klut_sub, thr_lower, thr_upper, v_cent, device,
+                 include_sparse=True, sparsity_threshold=0.99, n_sink=0):
+        self.lib = _lib.load()
+        self.bits, self.H, self.Lmax = int(bits), int(num_heads), int(max_len)
+        if self.Lmax % 4:
+            raise ValueError("max_len must be a multiple of 4 (TMA row pitch)")
+        self.hidden = self.H * HEAD_DIM
+        self.device = torch.device(device)
+        self.include_sparse = include_sparse
+        self.n_each = n_outliers_each(self.hidden, sparsity_threshold)
+        self.n_out = 2 * self.n_each
+        W = HEAD_DIM * bits // 32
+        dev = self.device
+        self.kcache = torch.zeros((self.H, W, self.Lmax), dtype=torch.int32, device=dev)
+        self.vcache = torch.zeros((self.H, W, self.Lmax), dtype=torch.int32, device=dev)
+        self.klut = klut.contiguous()
+        self.klut_sub = (klut_sub if klut_sub is not None else klut).contiguous()
+        self.thr_lower, self.thr_upper = thr_lower.contiguous(), thr_upper.contiguous()
+        self.v_cent = v_cent.contiguous()
+        self.vlut = torch.zeros((self.Lmax, 2 ** bits), dtype=torch.float32, device=dev)
+        self.k_outliers = torch.zeros((self.Lmax, self.n_out), dtype=torch.float32, device=dev)
+        self.k_outlier_idx = torch.zeros((self.Lmax, self.n_out), dtype=torch.int32, device=dev)
+        self.v_outliers = torch.zeros((self.Lmax, self.n_out), dtype=torch.float32, device=dev)
+        self.v_outlier_idx = torch.zeros((self.Lmax, self.n_out), dtype=torch.int32, device=dev)
+        self.len = 0          # tokens in the quantised cache
+        self.n_sink = int(n_sink)
+        self.sink_k = self.sink_v = None
+        self._scratch = None
+        self._out = torch.empty((self.H, HEAD_DIM), dtype=torch.float32, device=dev)
+
+    @classmethod
+    def from_luts(cls, bits, num_heads, max_len, klut, v_cent, device="cuda", include_sparse=True,
+                  sparsity_threshold=0.99, n_sink=0):
+        """klut: mapping with 'lut' [hidden, n] (and optional 'lut2'), 'thr_lower', 'thr_upper' (numpy or torch)."""
+        def t(x):
+            return torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(device).float().contiguous()
+        lut = t(klut["lut"]).view(num_heads * HEAD_DIM, -1)
+        lut2 = t(klut["lut2"]).view(num_heads * HEAD_DIM, -1) if klut.get("lut2") is not None else None
+        return cls(bits, num_heads, max_len, lut, lut2, t(klut["thr_lower"]), t(klut["thr_upper"]),
+                   t(np.sort(np.asarray(v_cent.cpu() if torch.is_tensor(v_cent) else v_cent).ravel())), device,
+                   include_sparse, sparsity_threshold, n_sink)
+
+    def reset(self):
+        self.len = 0
+        for x in (self.kcache, self.vcache, self.vlut, self.k_outliers, self.k_outlier_idx, self.v_outliers,
+                  self.v_outlier_idx):
+            x.zero_()
+
+    def set_sinks(self, sink_k, sink_v):
+        """fp16 attention-sink side caches (modeling_llama.py:1464-1466): sink_k [H,128,n] post-RoPE, sink_v [H,n,128]."""
+        assert sink_k.dtype == torch.float16 and sink_v.dtype == torch.float16
+        assert tuple(sink_k.shape) == (self.H, HEAD_DIM, self.n_sink) and tuple(sink_v.shape) == (self.H, self.n_sink, HEAD_DIM)
+        self.sink_k, self.sink_v = sink_k.contiguous(), sink_v.contiguous()
+
+    def load_state(self, src):
+        """Copy a pre-built cache (any object exposing kwords/vwords/vlut/k_out/k_idx/v_out/v_idx/len as arrays)."""
+        def put(dst, a):
+            dst.copy_(torch.as_tensor(np.ascontiguousarray(a)).view(dst.shape) if not torch.is_tensor(a) else a.view(dst.shape))
+        put(self.kcache, src.kwords); put(self.vcache, src.vwords); put(self.vlut, src.vlut)
+        put(self.k_outliers, src.k_out); put(self.k_outlier_idx, src.k_idx)
+        put(self.v_outliers, src.v_out); put(self.v_outlier_idx, src.v_idx)
+        self.len = int(src.len)
+
+    def append(self, k_new, v_new):
+        """Quantise + pack + outlier split of one token's K and V, entirely on the device (one launch)."""
+        if not self.include_sparse:
+            raise NotImplementedError("dense-only native append: use QuantK/QuantV (legacy ops)")
+        if self.len >= self.Lmax:
+            raise IndexError("cache full")
+        s = torch.cuda.current_stream().cuda_stream
+        _lib.check(self.lib.kvq_append_kv_fused(
+            self.bits, self.H, self.Lmax, self.len, self.n_each,
+            qc._f32(k_new, "k_new"), self.kcache.data_ptr(), self.klut.data_ptr(), self.klut_sub.data_ptr(),
+            self.thr_lower.data_ptr(), self.thr_upper.data_ptr(), self.k_outliers.data_ptr(),
+            self.k_outlier_idx.data_ptr(), qc._f32(v_new, "v_new"), self.vcache.data_ptr(), self.v_cent.data_ptr(),
+            self.vlut.data_ptr(), self.v_outliers.data_ptr(), self.v_outlier_idx.data_ptr(), s), "kvq_append_kv_fused")
+        self.len += 1
+
+    def attend(self, q, rope_theta=10000.0, out=None):
+        """softmax(q.K^T/sqrt(128)).V over sinks + quantised slots.  q: f32 [H,128] already rotated at its own
+        position.  Returns f32 [H,128]."""
+        L = self.len
+        need = self.lib.kvq_attend_scratch_bytes(self.H, max(L, 1))
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=self.device)
+        rope, npos = qc.rope_table(self.device, rope_theta, L + self.n_sink + 1)
+        out = self._out if out is None else out
+        sp = self.include_sparse
+        ns = self.n_sink if self.sink_k is not None else 0
+        _lib.check(self.lib.kvq_attend(
+            self.bits, qc._f32(q, "q"), self.kcache.data_ptr(), self.klut.data_ptr(),
+            self.k_outliers.data_ptr() if sp else None, self.k_outlier_idx.data_ptr() if sp else None,
+            self.vcache.data_ptr(), self.vlut.data_ptr(),
+            self.v_outliers.data_ptr() if sp else None, self.v_outlier_idx.data_ptr() if sp else None,
+            self.n_out, self.H, self.Lmax, L, rope.data_ptr(), npos, self.n_sink,
+            self.sink_k.data_ptr() if ns else None, self.sink_v.data_ptr() if ns else None, ns,
+            out.data_ptr(), self._scratch.data_ptr(), torch.cuda.current_stream().cuda_stream), "kvq_attend")
+        return out
+
+    def bytes_per_token(self):
+        """Algorithmic HBM bytes one decode step reads per cached token (SURVEY.md 8d formula)."""
+        b = 2 * self.H * HEAD_DIM * self.bits // 8 + 4 * 2 ** self.bits
+        if self.include_sparse:
+            b += 2 * self.n_out * 8
+        return b
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# reference-interface mirrors
+# -----------------------------------------------------------------------------------------------------------------
+class QuantK(torch.nn.Module):
+    """Mirror of the reference's QuantK (modeling_llama.py:352-975)."""
+
+    def __init__(self, bits=2, hidden_size=4096, num_heads=32, max_position_embeddings=-1, include_sparse=False,
+                 sparsity_threshold=0.99, rope_theta=10000, use_orig_sparse=False, first_few_fp16=0):
+        super().__init__()
+        self.hidden_size, self.num_heads = hidden_size, num_heads
+        self.head_dim = hidden_size // num_heads
+        self.bits = bits
+        self.lut = None
+        self.lookup_table = None
+        self.zeropoint = None
+        self.sparsity_threshold = sparsity_threshold
+        self.include_sparse = include_sparse
+        self.outlier_threshold_upper = self.outlier_threshold_lower = None
+        self.max_len = max_position_embeddings
+        self.klen = 0
+        self.kcache = torch.zeros((num_heads, (self.head_dim // 32) * bits, self.max_len), dtype=torch.int).cuda()
+        self.n_out = 2 * n_outliers_each(hidden_size, sparsity_threshold)  # reference hard-codes 42 (ML.py:396)
+        if include_sparse:
+            self.outliers = torch.zeros((self.max_len, self.n_out), dtype=torch.float).cuda()
+            self.outlier_indices = torch.zeros((self.max_len, self.n_out), dtype=torch.int).cuda()
+        self.rope_theta = rope_theta
+        self.rows = torch.tensor([]).cuda(); self.cols = torch.tensor([]).cuda()
+        self.vals = torch.tensor([]).cuda(); self.start_rows = torch.tensor([]).cuda()
+        self.num_threads = -1
+        self.use_orig_sparse = use_orig_sparse
+        self.first_few_fp16 = first_few_fp16
+        self.norm = False
+        self.lookup_table2 = None
+
+    def reset(self):
+        self.klen = 0
+        self.kcache.zero_()
+        if self.include_sparse:
+            if self.use_orig_sparse:
+                self.rows = torch.tensor([]).cuda(); self.cols = torch.tensor([]).cuda()
+                self.vals = torch.tensor([]).cuda(); self.start_rows = torch.tensor([]).cuda()
+                self.num_threads = -1
+            else:
+                self.outliers.zero_()
+                self.outlier_indices.zero_()
+
+    def load_lookup_table(self, quantizer, include_sparse=True, sparsity_threshold=0.99, norm=False):
+        """quantizer: one `quantizers.pickle` entry (upper, lower, [centroids], [normscale, normoffset])."""
+        self.include_sparse, self.sparsity_threshold, self.norm = include_sparse, sparsity_threshold, norm
+        ns = no = None
+        if norm:
+            ns, no = float(quantizer[3]), float(quantizer[4])
+            self.normscale, self.normoffset = quantizer[3], quantizer[4]
+        t = build_k_lookup_table(quantizer[0], quantizer[1], quantizer[2][0], self.num_heads, ns, no,
+                                 device=self.kcache.device)
+        self.lut = t["cent"]
+        self.lookup_table = t["lut"]
+        self.lookup_table2 = t["lut2"]
+        self.zeropoint = t["zeropoint"]
+        self.outlier_threshold_upper, self.outlier_threshold_lower = t["thr_upper"], t["thr_lower"]
+
+    def _op(self, fmt):
+        return getattr(qc, fmt % self.bits)
+
+    def _outlier_rows(self, k_tok, rescaled_tok):
+        """k_tok, rescaled_tok: [T, hidden].  Device version of modeling_llama.py:706-751 / 934-971."""
+        n_each = n_outliers_each(self.hidden_size, self.sparsity_threshold)
+        up_r, up_i = torch.topk(rescaled_tok, n_each, dim=-1)
+        lo_r, lo_i = torch.topk(rescaled_tok, n_each, dim=-1, largest=False)
+        numvals = 2 ** self.bits
+        lut = (self.lookup_table2 if self.norm else self.lookup_table).reshape(-1, numvals)
+        up_v = torch.gather(k_tok, 1, up_i) - lut[up_i, numvals - 1]
+        lo_v = torch.gather(k_tok, 1, lo_i) - lut[lo_i, 0]
+        zer = torch.cat((up_r <= 1, lo_r >= -1), dim=-1)
+        vals = torch.cat((up_v, lo_v), dim=-1)
+        idx = torch.cat((up_i, lo_i), dim=-1)
+        idx, order = idx.sort(dim=-1)
+        vals = torch.gather(vals, 1, order)
+        vals[torch.gather(zer, 1, order)] = 0
+        return vals, idx.int()
+
+    def forward_fused_sparse(self, q, k):
+        """Append the new pre-RoPE key and return q.K^T over the compressed cache: fp16 [num_heads, B, klen]."""
+        k = k.flatten().float()
+        q = q.float().transpose(0, 1).contiguous()
+        slot = self.klen - self.first_few_fp16
+        if self.include_sparse:
+            resc = k.clone()
+            self._op("vecquant%dappendvecKsparse")(self.kcache, self.lookup_table, k, resc,
+                                                    self.outlier_threshold_lower, self.outlier_threshold_upper, slot)
+            vals, idx = self._outlier_rows(k[None], resc[None])
+            self.outliers[slot] = vals[0]
+            self.outlier_indices[slot] = idx[0]
+        else:
+            self._op("vecquant%dappendvecK")(self.kcache, self.lookup_table, k, slot)
+        self.klen += 1
+        L = self.klen - self.first_few_fp16
+        mul = torch.zeros((q.shape[0], q.shape[1], L), dtype=torch.float, device=q.device)
+        lut = self.lookup_table2 if (self.norm and self.lookup_table2 is not None) else self.lookup_table
+        if self.include_sparse:
+            self._op("vecquant%dmatmul_nuq_perchannel_transposed_rope_mha_batched_fused_opt2")(
+                q, self.kcache, mul, lut, L, self.outliers, self.outlier_indices, self.rope_theta, self.first_few_fp16)
+        else:
+            self._op("vecquant%dmatmul_nuq_perchannel_transposed_rope_mha_batched_fused_opt")(
+                q, self.kcache, mul, lut, L, self.rope_theta, self.first_few_fp16)
+        return mul.transpose(0, 1).contiguous().half()
+
+    def parallel_pack(self, k):
+        """Prefill: k [H,128,T] pre-RoPE keys -> slots 0..T-1 (modeling_llama.py:879-975)."""
+        assert self.include_sparse
+        k = k.float().contiguous()
+        T = k.shape[-1]
+        self.klen += T
+        resc = k.clone()
+        self._op("vecquant%dappendvecKsparseParallel")(self.kcache, self.lookup_table, k, resc,
+                                                        self.outlier_threshold_lower, self.outlier_threshold_upper)
+        vals, idx = self._outlier_rows(k.reshape(-1, T).t().contiguous(), resc.reshape(-1, T).t().contiguous())
+        self.outliers[:self.klen] = vals
+        self.outlier_indices[:self.klen] = idx
+
+
+class QuantV(torch.nn.Module):
+    """Mirror of the reference's QuantV (modeling_llama.py:978-1385)."""
+
+    def __init__(self, bits=2, hidden_size=4096, num_heads=32, max_position_embeddings=-1, include_sparse=False,
+                 sparsity_threshold=0.99, first_few_fp16=0):
+        super().__init__()
+        self.hidden_size, self.num_heads = hidden_size, num_heads
+        self.head_dim = hidden_size // num_heads
+        self.bits = bits
+        self.lut = None
+        self.include_sparse, self.sparsity_threshold = include_sparse, sparsity_threshold
+        self.max_len = max_position_embeddings
+        self.vlen = 0
+        self.vcache = torch.zeros((num_heads, (self.head_dim // 32) * bits, self.max_len), dtype=torch.int).cuda()
+        self.lookup_table = torch.zeros((self.max_len, 2 ** bits), dtype=torch.float).cuda()
+        self.n_out = 2 * n_outliers_each(hidden_size, sparsity_threshold)
+        if include_sparse:
+            self.outliers = torch.zeros((self.max_len, self.n_out), dtype=torch.float).cuda()
+            self.outlier_indices = torch.zeros((self.max_len, self.n_out), dtype=torch.int).cuda()
+        self.first_few_fp16 = first_few_fp16
+        self.norm = False
+
+    def reset(self):
+        self.vlen = 0
+        self.vcache.zero_()
+        self.lookup_table.zero_()
+        if self.include_sparse:
+            self.outliers.zero_()
+            self.outlier_indices.zero_()
+
+    def load_lookup_table(self, quantizer, include_sparse=True, sparsity_threshold=0.99, norm=False):
+        """Only the sorted centroids are kept (modeling_llama.py:1054-1055); the per-token LUT is built on append."""
+        self.lut = torch.as_tensor(np.asarray(quantizer[2][0], dtype=np.float32)).flatten().sort().values.to(self.vcache.device)
+        self.include_sparse, self.sparsity_threshold, self.norm = include_sparse, sparsity_threshold, norm
+
+    def _op(self, fmt):
+        return getattr(qc, fmt % self.bits)
+
+    def topk_thresholds(self, v):
+        """Device version of modeling_llama.py:1803-1820: (upper_vals, upper_idx, lower_vals, lower_idx), k = n_each+1."""
+        kk = n_outliers_each(self.hidden_size, self.sparsity_threshold) + 1
+        uv, ui = torch.topk(v, kk, dim=-1)
+        lv, li = torch.topk(v, kk, dim=-1, largest=False)
+        return uv, ui, lv, li
+
+    def forward_fused_sparse(self, score, v, upper_outlier_vals=None, upper_outlier_indices=None,
+                             lower_outlier_vals=None, lower_outlier_indices=None):
+        """Append the new value vector and return score.V: fp16 [num_heads, B, 128]."""
+        score = score.float()
+        v = v.flatten().float()
+        slot = self.vlen - self.first_few_fp16
+        zp_idx = {4: 7, 3: 3, 2: 1}[self.bits]
+        if self.include_sparse:
+            if upper_outlier_vals is None:
+                upper_outlier_vals, upper_outlier_indices, lower_outlier_vals, lower_outlier_indices = self.topk_thresholds(v)
+            maxval, minval = upper_outlier_vals[-1], lower_outlier_vals[-1]
+            uv, lv = upper_outlier_vals[:-1], lower_outlier_vals[:-1]
+            ui, li = upper_outlier_indices[:-1], lower_outlier_indices[:-1]
+            offset = (maxval + minval) / 2
+            sf = (maxval - minval) / 2
+        else:
+            maxval, minval = v.max(), v.min()
+            offset = (maxval + minval) / 2
+            sf = (maxval - minval) / 2
+        lut_t = self.lut.float() * sf.float() + offset.float()   # device math, no .item() sync
+        self.lookup_table[slot] = lut_t
+        score = score.transpose(0, 1).contiguous()
+        if self.include_sparse:
+            zeropoint = lut_t[zp_idx]
+            self._op("vecquant%dappendvecVsparse")(self.vcache, self.lookup_table, v, zeropoint, minval, maxval, slot)
+            vals = torch.cat((uv, lv), dim=-1) - zeropoint
+            idx = torch.cat((ui, li), dim=-1)
+            idx, order = idx.sort()
+            self.outliers[slot] = vals[order]
+            self.outlier_indices[slot] = idx.int()
+        else:
+            self._op("vecquant%dappendvecV")(self.vcache, self.lookup_table, v, slot)
+        self.vlen += 1
+        L = self.vlen - self.first_few_fp16
+        mul = torch.zeros((score.shape[0], score.shape[1], self.head_dim), dtype=torch.float, device=score.device)
+        if self.include_sparse:
+            self._op("vecquant%dmatmul_nuq_perchannel_transposed_mha_batched_fused_opt2")(
+                score, self.vcache, mul, self.lookup_table, L, self.outliers, self.outlier_indices)
+        else:
+            self._op("vecquant%dmatmul_nuq_perchannel_transposed_mha_batched_fused_opt")(
+                score, self.vcache, mul, self.lookup_table, L)
+        return mul.transpose(0, 1).contiguous().half()
+
+    def parallel_pack(self, v, upper_outlier_vals, upper_outlier_indices, lower_outlier_vals, lower_outlier_indices):
+        """Prefill: v [H,128,T]; top-k tensors [T, n_each+1] (modeling_llama.py:1294-1385)."""
+        assert self.include_sparse
+        v = v.float().contiguous()
+        T = v.shape[-1]
+        zp_idx = {4: 7, 3: 3, 2: 1}[self.bits]
+        maxval, minval = upper_outlier_vals[:, -1], lower_outlier_vals[:, -1]
+        offset = ((maxval + minval) / 2)[:, None]
+        sf = ((maxval - minval) / 2)[:, None]
+        lut = self.lut.float()[None, :] * sf + offset
+        self.lookup_table[self.vlen:self.vlen + T] = lut
+        self._op("vecquant%dappendvecVsparseParallel")(self.vcache, self.lookup_table, v, minval.contiguous(),
+                                                        maxval.contiguous())
+        vals = torch.cat((upper_outlier_vals[:, :-1], lower_outlier_vals[:, :-1]), dim=-1) - lut[:, zp_idx:zp_idx + 1]
+        idx = torch.cat((upper_outlier_indices[:, :-1], lower_outlier_indices[:, :-1]), dim=-1)
+        idx, order = idx.sort(dim=-1)
+        self.outliers[self.vlen:self.vlen + T] = torch.gather(vals, 1, order)
+        self.outlier_indices[self.vlen:self.vlen + T] = idx.int()
+        self.vlen += T
+
+
+def attention_decode_reference_chain(kcache: QuantK, vcache: QuantV, q, k, v, head_dim=HEAD_DIM):
+    """The reference's decode attention chain around the two managers (modeling_llama.py:1963-1999, no sinks):
+    scores.half()/sqrt(d) -> fp32 softmax -> .half() -> V."""
+    s = kcache.forward_fused_sparse(q, k)               # [H,1,L] fp16
+    s = s.unsqueeze(0) / math.sqrt(head_dim)
+    p = torch.nn.functional.softmax(s, dim=-1, dtype=torch.float32).to(torch.float16).squeeze(0)
+    return vcache.forward_fused_sparse(p, v)            # [H,1,128] fp16

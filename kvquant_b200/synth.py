@@ -93,3 +93,49 @@ def calibrate(spec: SynthSpec, bits: int, calib_tokens=2048, seed=1234):
         "v": (np.quantile(v, 0.995, axis=0).astype(np.float32),
               np.quantile(v, 0.005, axis=0).astype(np.float32), [vcent.reshape(n, 1)]),
     }
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU-side synthetic cache fill (bench / probes): same distributions, generated with torch on the device
+# ---------------------------------------------------------------------------------------------------------------
+def fill_layer_cache_gpu(lc, spec: SynthSpec, L: int, seed: int = 0, chunk: int = 8192):
+    """Fill a kvquant_b200.cache.LayerCache with L synthetic tokens through the real prefill packers
+    (quant_cuda.vecquantNappendvec{K,V}sparseParallel + device top-k), `chunk` tokens at a time; the first chunk is
+    packed for real, later chunks are packed into a scratch cache and copied to their slots."""
+    import torch
+    from . import cache as kc
+    dev = lc.device
+    H, hidden, bits = lc.H, lc.hidden, lc.bits
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + seed)
+    mu = torch.as_tensor(spec.mu, device=dev)
+    sigma = torch.as_tensor(spec.sigma, device=dev)
+    qk = kc.QuantK(bits, hidden, H, max_position_embeddings=chunk, include_sparse=True)
+    qv = kc.QuantV(bits, hidden, H, max_position_embeddings=chunk, include_sparse=True)
+    qk.lookup_table = lc.klut.view(H, 128, -1)
+    qk.lookup_table2 = None
+    qk.outlier_threshold_lower, qk.outlier_threshold_upper = lc.thr_lower, lc.thr_upper
+    qv.lut = lc.v_cent
+    done = 0
+    while done < L:
+        T = min(chunk, L - done)
+        k = torch.randn((T, hidden), generator=g, device=dev) * sigma + mu
+        tail = torch.rand((T, hidden), generator=g, device=dev) < 0.005
+        k = k + tail * torch.randn((T, hidden), generator=g, device=dev) * 6.0 * sigma
+        st = torch.exp(torch.randn((T, 1), generator=g, device=dev) * 0.3)
+        v = torch.randn((T, hidden), generator=g, device=dev) * st
+        tail = torch.rand((T, hidden), generator=g, device=dev) < 0.005
+        v = v + tail * torch.randn((T, hidden), generator=g, device=dev) * 6.0 * st
+        qk.reset(); qv.reset()
+        qk.parallel_pack(k.t().contiguous().view(H, 128, T))
+        uv, ui, lv, li = qv.topk_thresholds(v)
+        qv.parallel_pack(v.t().contiguous().view(H, 128, T), uv, ui, lv, li)
+        sl = slice(done, done + T)
+        lc.kcache[:, :, sl] = qk.kcache[:, :, :T]
+        lc.vcache[:, :, sl] = qv.vcache[:, :, :T]
+        lc.vlut[sl] = qv.lookup_table[:T]
+        lc.k_outliers[sl] = qk.outliers[:T]; lc.k_outlier_idx[sl] = qk.outlier_indices[:T]
+        lc.v_outliers[sl] = qv.outliers[:T]; lc.v_outlier_idx[sl] = qv.outlier_indices[:T]
+        done += T
+    lc.len = L
+    return lc

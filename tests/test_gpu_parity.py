@@ -1,0 +1,252 @@
+"""GPU parity tests: every op is called through the reference-facing `quant_cuda` surface (which goes through the
+C ABI) and compared with the CPU oracle on the same seeded inputs.
+
+Tolerances
+  * packed codes, outlier indices, V thresholds: BIT-EXACT;
+  * fp32 element-wise results (rescaled, outlier values, V LUT rows): bit-exact / <= 1 ulp;
+  * matvec results: norm-wise relative error <= 1e-4 against the float64 oracle (fp32 accumulation order differs;
+    the reference itself accumulates with atomics in a non-deterministic order);
+  * fused attention output: <= 1e-3 relative (north_star) against the oracle chain, both with and without the
+    reference's fp16 round trips.
+"""
+import numpy as np
+import pytest
+import torch
+
+from _util import O, oracle_cache, quantizer, rel_err, spec
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _qc():
+    import quant_cuda
+    return quant_cuda
+
+
+def _op(name_fmt, bits):
+    return getattr(_qc(), name_fmt % bits)
+
+
+def cu(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+def device_cache(c):
+    """Upload an OracleCache as the tensors QuantK/QuantV own (modeling_llama.py:392-397,1011-1019)."""
+    H, W = c.H, c.hidden * c.bits // 32 // c.H
+    d = dict(
+        kcache=cu(c.kwords.reshape(H, W, c.Lmax)), vcache=cu(c.vwords.reshape(H, W, c.Lmax)),
+        klut=cu(c.klut["lut"].reshape(H, 128, -1)), vlut=cu(c.vlut),
+        k_out=cu(c.k_out), k_idx=cu(c.k_idx), v_out=cu(c.v_out), v_idx=cu(c.v_idx))
+    return d
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# appends
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bits", [4, 3, 2])
+def test_append_k_and_v_single_token_bit_exact(bits):
+    klut, vcent = quantizer(bits)
+    sp = spec()
+    H, W, Lmax = 32, 128 * bits // 32, 96
+    k = sp.k_tokens(3, seed=21)
+    v = sp.v_tokens(3, seed=22)
+    kc = torch.zeros((H, W, Lmax), dtype=torch.int32, device=DEV)
+    kc2 = torch.zeros_like(kc)
+    vc = torch.zeros_like(kc)
+    vc2 = torch.zeros_like(kc)
+    lut = cu(klut["lut"].reshape(H, 128, -1))
+    vlut = torch.zeros((Lmax, 2 ** bits), dtype=torch.float32, device=DEV)
+    slots = [0, 41, Lmax - 1]
+    for i, slot in enumerate(slots):
+        kv, vv = cu(k[i]), cu(v[i])
+        _op("vecquant%dappendvecK", bits)(kc, lut, kv, slot)
+        resc = kv.clone()
+        _op("vecquant%dappendvecKsparse", bits)(kc2, lut, kv, resc, cu(klut["thr_lower"]), cu(klut["thr_upper"]), slot)
+        want = O.pack_codes(O.append_k_codes(k[i], klut["lut"]), bits)[:, 0]
+        assert np.array_equal(kc.cpu().numpy().reshape(-1, Lmax)[:, slot], want)
+        assert np.array_equal(kc2.cpu().numpy().reshape(-1, Lmax)[:, slot], want)
+        r = O.k_outliers_rescaled(k[i], klut["thr_lower"], klut["thr_upper"])
+        assert np.array_equal(resc.cpu().numpy(), r)
+        # V: dense (min/max LUT) and sparse (22nd order statistics, zero-point for outliers)
+        hi, lo, ui, li = O.v_thresholds(v[i], 21)
+        lt = O.v_token_lut(vcent, hi, lo)
+        vlut[slot] = cu(lt)
+        _op("vecquant%dappendvecV", bits)(vc, vlut, vv, slot)
+        _op("vecquant%dappendvecVsparse", bits)(vc2, vlut, vv, float(lt[O.zero_point_code(bits)]), float(lo), float(hi), slot)
+        assert np.array_equal(vc.cpu().numpy().reshape(-1, Lmax)[:, slot],
+                              O.pack_codes(O.append_v_codes(v[i], lt, bits), bits)[:, 0])
+        assert np.array_equal(vc2.cpu().numpy().reshape(-1, Lmax)[:, slot],
+                              O.pack_codes(O.append_v_codes(v[i], lt, bits, lo, hi), bits)[:, 0])
+    # untouched slots stay zero; appending twice ADDS (reference atomicAdd semantics)
+    mask = np.ones(Lmax, bool)
+    mask[slots] = False
+    assert not kc.cpu().numpy()[:, :, mask].any()
+    before = kc.cpu().numpy().reshape(-1, Lmax)[:, 0].copy()
+    _op("vecquant%dappendvecK", bits)(kc, lut, cu(k[0]), 0)
+    after = kc.cpu().numpy().reshape(-1, Lmax)[:, 0]
+    assert np.array_equal(after.view(np.uint32), (before.view(np.uint32) * 2).astype(np.uint32))
+
+
+@pytest.mark.parametrize("bits", [4, 3, 2])
+def test_append_parallel_prefill_bit_exact(bits):
+    klut, vcent = quantizer(bits)
+    sp = spec()
+    H, W, Lmax, T = 32, 128 * bits // 32, 256, 173
+    k = sp.k_tokens(T, seed=31)  # [T, hidden]
+    v = sp.v_tokens(T, seed=32)
+    kc = torch.zeros((H, W, Lmax), dtype=torch.int32, device=DEV)
+    vc = torch.zeros_like(kc)
+    kin = cu(k.T.reshape(H, 128, T))
+    resc = kin.clone()
+    _op("vecquant%dappendvecKsparseParallel", bits)(kc, cu(klut["lut"].reshape(H, 128, -1)), kin, resc,
+                                                     cu(klut["thr_lower"]), cu(klut["thr_upper"]))
+    want = O.pack_codes(O.append_k_codes(k.T, klut["lut"]), bits)
+    got = kc.cpu().numpy().reshape(-1, Lmax)
+    assert np.array_equal(got[:, :T], want) and not got[:, T:].any()
+    assert np.array_equal(resc.cpu().numpy().reshape(-1, T), O.k_outliers_rescaled(k.T, klut["thr_lower"], klut["thr_upper"]))
+    # V
+    vlut = np.zeros((Lmax, 2 ** bits), np.float32)
+    lo = np.zeros(T, np.float32)
+    hi = np.zeros(T, np.float32)
+    codes = np.zeros((4096, T), np.uint8)
+    for t in range(T):
+        hi[t], lo[t], _, _ = O.v_thresholds(v[t], 21)
+        vlut[t] = O.v_token_lut(vcent, hi[t], lo[t])
+        codes[:, t] = O.append_v_codes(v[t], vlut[t], bits, lo[t], hi[t])
+    _op("vecquant%dappendvecVsparseParallel", bits)(vc, cu(vlut), cu(v.T.reshape(H, 128, T)), cu(lo), cu(hi))
+    got = vc.cpu().numpy().reshape(-1, Lmax)
+    assert np.array_equal(got[:, :T], O.pack_codes(codes, bits)) and not got[:, T:].any()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# matvecs (legacy surface)
+# ---------------------------------------------------------------------------------------------------------------
+CASES = [(4, 1100, True), (4, 300, False), (3, 611, True), (3, 200, False), (2, 530, True), (2, 33, False), (4, 1, True)]
+
+
+@pytest.mark.parametrize("bits,L,sparse", CASES)
+def test_k_matvec_matches_oracle(bits, L, sparse):
+    c, k, v = oracle_cache(bits, L, sparse=sparse)
+    d = device_cache(c)
+    H = c.H
+    for theta, off in ((10000.0, 0), (1000000.0, 5)):
+        q = O.rope_rotate_q(spec().q_vec(5), L + off, theta)
+        want = c.k_scores(q, theta, off)
+        mul = torch.zeros((1, H, L), dtype=torch.float32, device=DEV)
+        if sparse:
+            _op("vecquant%dmatmul_nuq_perchannel_transposed_rope_mha_batched_fused_opt2", bits)(
+                cu(q[None]), d["kcache"], mul, d["klut"], L, d["k_out"], d["k_idx"], theta, off)
+        else:
+            _op("vecquant%dmatmul_nuq_perchannel_transposed_rope_mha_batched_fused_opt", bits)(
+                cu(q[None]), d["kcache"], mul, d["klut"], L, theta, off)
+        e_max, e_l2 = rel_err(mul.cpu().numpy()[0], want)
+        assert e_max < 1e-4 and e_l2 < 1e-4, (e_max, e_l2)
+        # accumulate semantics: calling again doubles the result (mul is in/out, modeling_llama.py:782)
+        if off == 0 and L == 300:
+            _op("vecquant%dmatmul_nuq_perchannel_transposed_rope_mha_batched_fused_opt", bits)(
+                cu(q[None]), d["kcache"], mul, d["klut"], L, theta, off)
+            assert rel_err(mul.cpu().numpy()[0], 2 * want)[0] < 1e-4
+
+
+@pytest.mark.parametrize("bits,L,sparse", CASES)
+def test_v_matvec_matches_oracle(bits, L, sparse):
+    c, k, v = oracle_cache(bits, L, sparse=sparse)
+    d = device_cache(c)
+    H = c.H
+    rng = np.random.default_rng(L)
+    p = O.softmax_f32(rng.standard_normal((H, L)).astype(np.float32) * 3).astype(np.float16).astype(np.float32)
+    want = c.v_output(p)
+    mul = torch.zeros((1, H, 128), dtype=torch.float32, device=DEV)
+    if sparse:
+        _op("vecquant%dmatmul_nuq_perchannel_transposed_mha_batched_fused_opt2", bits)(
+            cu(p[None]), d["vcache"], mul, d["vlut"], L, d["v_out"], d["v_idx"])
+    else:
+        _op("vecquant%dmatmul_nuq_perchannel_transposed_mha_batched_fused_opt", bits)(
+            cu(p[None]), d["vcache"], mul, d["vlut"], L)
+    e_max, e_l2 = rel_err(mul.cpu().numpy()[0], want)
+    assert e_max < 1e-4 and e_l2 < 1e-4, (e_max, e_l2)
+
+
+def test_batched_dense_ops():
+    c, k, v = oracle_cache(4, 300, sparse=False)
+    d = device_cache(c)
+    L, H, B = 300, 32, 3
+    qs = np.stack([O.rope_rotate_q(spec().q_vec(50 + b), L, 10000.0) for b in range(B)])
+    mul = torch.zeros((B, H, L), dtype=torch.float32, device=DEV)
+    _qc().vecquant4matmul_nuq_perchannel_transposed_rope_mha_batched_fused_opt(cu(qs), d["kcache"], mul, d["klut"], L, 10000.0, 0)
+    for b in range(B):
+        assert rel_err(mul.cpu().numpy()[b], c.k_scores(qs[b]))[0] < 1e-4
+    rng = np.random.default_rng(1)
+    ps = O.softmax_f32(rng.standard_normal((B, H, L)).astype(np.float32))
+    out = torch.zeros((B, H, 128), dtype=torch.float32, device=DEV)
+    _qc().vecquant4matmul_nuq_perchannel_transposed_mha_batched_fused_opt(cu(ps), d["vcache"], out, d["vlut"], L)
+    for b in range(B):
+        assert rel_err(out.cpu().numpy()[b], c.v_output(ps[b]))[0] < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# native fused ops
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bits", [4, 3, 2])
+def test_fused_device_append_matches_host_topk_path(bits):
+    from kvquant_b200.cache import LayerCache
+    klut, vcent = quantizer(bits)
+    L = 40
+    c, k, v = oracle_cache(bits, L)
+    lc = LayerCache.from_luts(bits, 32, c.Lmax, klut, vcent, device=DEV)
+    for t in range(L):
+        lc.append(cu(k[t]), cu(v[t]))
+    assert np.array_equal(lc.kcache.cpu().numpy().reshape(-1, c.Lmax), c.kwords)
+    assert np.array_equal(lc.vcache.cpu().numpy().reshape(-1, c.Lmax), c.vwords)
+    assert np.array_equal(lc.k_outlier_idx.cpu().numpy(), c.k_idx)
+    assert np.array_equal(lc.v_outlier_idx.cpu().numpy(), c.v_idx)
+    assert np.array_equal(lc.k_outliers.cpu().numpy(), c.k_out)
+    assert np.array_equal(lc.v_outliers.cpu().numpy(), c.v_out)
+    assert np.array_equal(lc.vlut.cpu().numpy(), c.vlut)
+
+
+@pytest.mark.parametrize("bits,L,sparse,n_sink", [(4, 1100, True, 0), (3, 611, True, 5), (2, 530, True, 0),
+                                                   (4, 300, False, 3), (4, 1, True, 0)])
+def test_fused_attend_within_1e3_of_oracle_chain(bits, L, sparse, n_sink):
+    from kvquant_b200.cache import LayerCache
+    c, k, v = oracle_cache(bits, L, sparse=sparse)
+    klut, vcent = quantizer(bits)
+    lc = LayerCache.from_luts(bits, 32, c.Lmax, klut, vcent, device=DEV, include_sparse=sparse, n_sink=n_sink)
+    lc.load_state(c)
+    sp = spec()
+    theta = 10000.0
+    q = O.rope_rotate_q(sp.q_vec(9), L + n_sink, theta)
+    sink_scores = None
+    if n_sink:
+        ks = np.stack([O.rope_rotate_q(sp.k_tokens(n_sink, 77)[i].reshape(32, 128), i, theta) for i in range(n_sink)])
+        vs = sp.v_tokens(n_sink, 78).reshape(n_sink, 32, 128)
+        ks16 = ks.astype(np.float16)            # [n, H, 128]
+        vs16 = vs.astype(np.float16)
+        lc.set_sinks(cu(np.ascontiguousarray(ks16.transpose(1, 2, 0))), cu(np.ascontiguousarray(vs16.transpose(1, 0, 2))))
+        sink_scores = np.einsum("hc,nhc->hn", q.astype(np.float64), ks16.astype(np.float64))
+    s = c.k_scores(q, theta, n_sink)
+
+    def v_fn(p):
+        return c.v_output(p)
+
+    p_id, o_id = O.attend_ideal(s, v_fn, sink_scores=None if sink_scores is None else sink_scores / np.sqrt(128) * np.sqrt(128))
+    if n_sink:
+        # ideal chain with sinks: scores concatenated in front, V contribution added
+        sc = np.concatenate([sink_scores, s], axis=-1) / np.sqrt(128)
+        m = sc.max(-1, keepdims=True)
+        e = np.exp(sc - m)
+        p = e / e.sum(-1, keepdims=True)
+        o_id = c.v_output(p[:, n_sink:]) + np.einsum("hn,nhc->hc", p[:, :n_sink], vs16.astype(np.float64))
+    out = lc.attend(cu(q), rope_theta=theta).cpu().numpy()
+    e_max, e_l2 = rel_err(out, o_id)
+    assert e_max < 1e-3 and e_l2 < 1e-3, (e_max, e_l2)
+    if not n_sink:
+        # and against the reference's own chain with its fp16 round trips (scores.half(), P.half(), out.half())
+        p16, o16 = O.attend_reference(s, v_fn, 32)
+        e_max, e_l2 = rel_err(out, o16.astype(np.float64))
+        assert e_max < 2e-3 and e_l2 < 1e-3, (e_max, e_l2)  # 2e-3: two fp16 ulps of the reference's own rounding
