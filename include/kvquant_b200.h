@@ -94,7 +94,8 @@ KVQ_API int kvq_rope_table_build(float* rope_cos_sin, float theta, int64_t n_pos
  *   mul[b,h,t] += sum_c (LUT[h,c,code] (+) outlier) * (cos(th_c*p)*q[b,h,c] + s_c*sin(th_c*p)*q[b,h,(c+64)%128])
  *   p = t + pos_offset.   q f32 [B,H,128]; mul f32 [B,H,L]; lut f32 [H*128,2^bits];
  *   outliers f32 [>=L, n_out], outlier_idx i32 [>=L, n_out] (flat channel index), B must be 1 when given;
- *   rope: table from kvq_rope_table_build covering positions [0, pos_offset+L), with row length rope_npos.
+ *   rope: table from kvq_rope_table_build(theta) covering positions [0, pos_offset+L), with row length rope_npos
+ *   (used by the dense kernel); theta: the same rope base, used by the outlier pre-pass (42 sincos per token).
  * kvq_v_matvec replaces ..._transposed_mha_batched_fused_opt (quant_cuda.cpp:214-224; kernel 3211-3433) and ..._opt2
  * (quant_cuda.cpp:226-238; + SPMV_ATOMIC_BALANCED 436-470):
  *   mul[b,h,c] += sum_t (LUT[t,code] (+) outlier) * score[b,h,t].   score f32 [B,H,L]; mul f32 [B,H,128].
@@ -103,7 +104,7 @@ KVQ_API int kvq_rope_table_build(float* rope_cos_sin, float theta, int64_t n_pos
 KVQ_API int kvq_k_matvec(int bits, const float* q, const int32_t* cache, float* mul, const float* lut,
                  int B, int H, int64_t Lmax, int64_t L,
                  const float* outliers, const int32_t* outlier_idx, int n_out,
-                 const float* rope_cos_sin, int64_t rope_npos, int pos_offset, void* stream);
+                 const float* rope_cos_sin, int64_t rope_npos, float theta, int pos_offset, void* stream);
 KVQ_API int kvq_v_matvec(int bits, const float* score, const int32_t* cache, float* mul, const float* lut_tok,
                  int B, int H, int64_t Lmax, int64_t L,
                  const float* outliers, const int32_t* outlier_idx, int n_out, void* stream);
@@ -123,7 +124,7 @@ KVQ_API int kvq_attend(int bits, const float* q,
                const int32_t* vcache, const float* vlut_tok,
                const float* v_outliers, const int32_t* v_outlier_idx,
                int n_out, int H, int64_t Lmax, int64_t L,
-               const float* rope_cos_sin, int64_t rope_npos, int pos_offset,
+               const float* rope_cos_sin, int64_t rope_npos, float theta, int pos_offset,
                const void* sink_k, const void* sink_v, int n_sink,
                float* out, void* scratch, void* stream);
 

@@ -144,7 +144,7 @@ class LayerCache:
             self.k_outliers.data_ptr() if sp else None, self.k_outlier_idx.data_ptr() if sp else None,
             self.vcache.data_ptr(), self.vlut.data_ptr(),
             self.v_outliers.data_ptr() if sp else None, self.v_outlier_idx.data_ptr() if sp else None,
-            self.n_out, self.H, self.Lmax, L, rope.data_ptr(), npos, self.n_sink,
+            self.n_out, self.H, self.Lmax, L, rope.data_ptr(), npos, float(rope_theta), self.n_sink,
             self.sink_k.data_ptr() if ns else None, self.sink_v.data_ptr() if ns else None, ns,
             out.data_ptr(), self._scratch.data_ptr(), torch.cuda.current_stream().cuda_stream), "kvq_attend")
         return out

@@ -42,24 +42,111 @@ struct KParams {
   const uint32_t* cache;     // [H*W, Lmax]
   float* out;                // [H, out_stride]
   const float* lut;          // [H*128, N]
-  const float* outliers;     // [>=L, n_out] or null
+  const float* outliers;     // [>=L, n_out] or null (consumed by k_outlier_kernel, not by the dense kernel)
   const int32_t* outlier_idx;
   const float2* rope;        // [64, rope_npos]
   float* gmax;               // [H] or null (fused mode: running max of scaled scores)
   int64_t Lmax, L, out_stride, rope_npos;
   int H, n_out, pos_offset, tiles_per_cta;
-  float scale;               // applied to S before store (fused mode); 1 for legacy
-  int accumulate;            // 1: out += S (legacy), 0: out = S*scale
+  float scale;               // applied before the store (fused mode: 1/sqrt(128)); 1 for legacy
+  int accumulate;            // 1: out = (out + S)*scale, 0: out = S*scale
 };
+
+// compile-time loop (immediate LDS offsets and PRMT selectors need constant expressions)
+template <int K> struct IC { static constexpr int v = K; };
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (B < E) { f(IC<B>{}); static_for<B + 1, E>(f); }
+}
+// 8-byte shared load at [addr + IMM] (addr is a 32-bit shared-window address)
+template <int IMM>
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+  float2 v;
+  asm("ld.shared.v2.f32 {%0,%1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(addr), "n"(IMM));
+  return v;
+}
+// packed fp32 FMA (sm_100 FFMA2): acc.xy += a.xy * b.xy in one issue slot
+__device__ __forceinline__ void ffma2(float2& acc, const float2 a, const float2 b) {
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%0,%1};"
+      " fma.rn.f32x2 rc, ra, rb, rc; mov.b64 {%0,%1}, rc; }"
+      : "+f"(acc.x), "+f"(acc.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+}
+
+// One (head, 16-pair chunk A): 32 table lookups + 32 packed FMAs.  `base` = shared address of the head's table
+// (256-byte aligned, so a code*8 byte can be PRMT-ed / OR-ed into its low byte); channel offsets are immediates.
+//   4-bit / 2-bit: the codes of a word are pre-masked into byte lanes (4 resp. 8 logic ops per word), then ONE
+//                  PRMT per element builds the address           -> PRMT + LDS.64 + FFMA2 per element;
+//   3-bit:         one funnel shift + one LOP3 (and-or) per element (straddling codes come for free from the
+//                  funnel shift)                                  -> SHF + LOP3 + LDS.64 + FFMA2 per element.
+template <int BITS, int A>
+__device__ __forceinline__ float k_chunk(const uint32_t* __restrict__ wn, const uint32_t base, const float2* __restrict__ cs) {
+  constexpr int N = 1 << BITS;
+  float2 acc[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  if constexpr (BITS == 4) {
+    // wn[0..1]: channels 16A..16A+15, wn[2..3]: +64
+    static_for<0, 4>([&](auto iw) {
+      constexpr int wi = decltype(iw)::v;
+      constexpr int c0 = 16 * A + (wi & 1) * 8 + (wi >> 1) * kHalf;
+      const uint32_t e = (wn[wi] << 3) & 0x78787878u, o = (wn[wi] >> 1) & 0x78787878u;
+      static_for<0, 8>([&](auto ik) {
+        constexpr int k = decltype(ik)::v;
+        const uint32_t addr = __byte_perm((k & 1) ? o : e, base, 0x7650 | (k >> 1));
+        ffma2(acc[(wi >> 1) * 2 + (k & 1)], cs[(wi & 1) * 8 + k], lds_f2<(c0 + k) * N * 8>(addr));
+      });
+    });
+  } else if constexpr (BITS == 2) {
+    // wn[0]: channels 16A..16A+15, wn[1]: +64
+    static_for<0, 2>([&](auto iw) {
+      constexpr int wi = decltype(iw)::v;
+      constexpr int c0 = 16 * A + wi * kHalf;
+      const uint32_t m0 = (wn[wi] << 3) & 0x18181818u, m1 = (wn[wi] << 1) & 0x18181818u;
+      const uint32_t m2 = (wn[wi] >> 1) & 0x18181818u, m3 = (wn[wi] >> 3) & 0x18181818u;
+      static_for<0, 16>([&](auto ik) {
+        constexpr int k = decltype(ik)::v;
+        const uint32_t src = (k & 3) == 0 ? m0 : ((k & 3) == 1 ? m1 : ((k & 3) == 2 ? m2 : m3));
+        const uint32_t addr = __byte_perm(src, base, 0x7650 | (k >> 2));
+        ffma2(acc[wi * 2 + (k & 1)], cs[k], lds_f2<(c0 + k) * N * 8>(addr));
+      });
+    });
+  } else {
+    // wn[0..1]: the two words holding locs [16*(A&1), +16) of group A>>1; wn[2..3]: same for group (A>>1)+2
+    static_for<0, 2>([&](auto ih) {
+      constexpr int hf = decltype(ih)::v;
+      const uint32_t w0 = wn[2 * hf], w1 = wn[2 * hf + 1];
+      static_for<0, 16>([&](auto ik) {
+        constexpr int k = decltype(ik)::v;
+        constexpr int l = 16 * (A & 1) + k;               // position within the 32-channel group
+        constexpr int bitpos = 3 * l - 32 * ((A & 1) ? 1 : 0);  // bit offset relative to w0 (may be negative / >= 32)
+        constexpr int c = 16 * A + k + hf * kHalf;
+        uint32_t x;
+        if constexpr (bitpos < 0) {
+          // (A&1)==1 and the code starts in the previous word: cannot happen for l >= 16 (3*16 = 48 >= 32)
+          x = 0;
+        } else if constexpr (bitpos + 3 <= 32) {
+          x = (bitpos >= 3) ? (w0 >> (bitpos - 3)) : (w0 << (3 - bitpos));
+        } else if constexpr (bitpos < 32) {
+          x = __funnelshift_r(w0, w1, bitpos - 3);       // straddles w0 / w1
+        } else {
+          x = (bitpos - 32 >= 3) ? (w1 >> (bitpos - 32 - 3)) : (w1 << (3 - (bitpos - 32)));
+        }
+        const uint32_t addr = (x & 0x38u) | base;
+        ffma2(acc[hf * 2 + (k & 1)], cs[k], lds_f2<c * N * 8>(addr));
+      });
+    });
+  }
+  return (acc[0].x + acc[0].y) + (acc[1].x + acc[1].y) + (acc[2].x + acc[2].y) + (acc[3].x + acc[3].y);
+}
 
 template <int BITS>
 __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const KParams p) {
   using C = KCfg<BITS>;
   constexpr int N = C::N, W = C::W, G = C::G, TT = C::TT, NR = C::NR;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* s_tab = reinterpret_cast<float2*>(smem_raw);           // [G][128][N]
+  extern __shared__ unsigned char smem_raw[];
+  // table base must be 256-byte aligned (the low address byte carries code*8)
+  unsigned char* smem = smem_raw + ((256u - (smem_u32(smem_raw) & 255u)) & 255u);
+  float2* s_tab = reinterpret_cast<float2*>(smem);                 // [G][128][N]
   float* s_q = reinterpret_cast<float*>(s_tab + G * kHeadDim * N);  // [G][128]
-  float* s_part = s_q + G * kHeadDim;                            // [G][TT]
+  float* s_part = s_q + G * kHeadDim;                              // [G][TT]
 
   const int tid = threadIdx.x;
   const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
@@ -79,6 +166,7 @@ __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const
   }
   for (int i = tid; i < G * TT; i += C::kThreads) s_part[i] = 0.f;
   __syncthreads();
+  const uint32_t tab0 = smem_u32(s_tab);
 
   const int64_t tile0 = (int64_t)blockIdx.x * p.tiles_per_cta;
   for (int ti = 0; ti < p.tiles_per_cta; ++ti) {
@@ -86,35 +174,13 @@ __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const
     if (tbase >= p.L) break;
     const int64_t t = tbase + tid;
     const bool live = t < p.L;
-    const int ntok = (int)min((int64_t)TT, p.L - tbase);
-
-    // ---- outlier stream of this tile: rows [tbase, tbase+ntok) are contiguous in memory --------------------
-    if (p.outliers != nullptr) {
-      const int total = ntok * p.n_out;
-      const float* ov = p.outliers + tbase * p.n_out;
-      const int32_t* oi = p.outlier_idx + tbase * p.n_out;
-      for (int e = tid; e < total; e += C::kThreads) {
-        const float val = ov[e];
-        const int idx = oi[e];
-        const int hl = (idx >> 7) - h0;
-        if (val != 0.f && hl >= 0 && hl < nh) {
-          const int tl = e / p.n_out;
-          const int c = idx & (kHeadDim - 1);
-          const float2 cs = ld_keep_f2(p.rope + (int64_t)(c & (kHalf - 1)) * p.rope_npos + (tbase + tl + p.pos_offset), pol_keep);
-          const float qa = s_q[hl * kHeadDim + c];
-          const float qb = s_q[hl * kHeadDim + (c ^ kHalf)];
-          const float sg = (c < kHalf) ? 1.f : -1.f;
-          atomicAdd(&s_part[hl * TT + tl], val * (cs.x * qa + sg * cs.y * qb));
-        }
-      }
-    }
 
     // ---- dense part ---------------------------------------------------------------------------------------
     if (live) {
       const uint32_t* col = p.cache + (int64_t)h0 * W * p.Lmax + t;
       const float2* rp = p.rope + (t + p.pos_offset);
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
+      static_for<0, 4>([&](auto ia) {
+        constexpr int a = decltype(ia)::v;
         float2 cs[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) cs[i] = ld_keep_f2(rp + (int64_t)(16 * a + i) * p.rope_npos, pol_keep);
@@ -122,29 +188,18 @@ __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const
 #pragma unroll
         for (int i = 0; i < NR; ++i) wn[i] = ld_stream_u32(col + (int64_t)chunk_row<BITS>(a, i) * p.Lmax, pol_stream);
         for (int hl = 0; hl < nh; ++hl) {
-          uint32_t w[W];
+          uint32_t w[NR];
 #pragma unroll
-          for (int i = 0; i < NR; ++i) w[chunk_row<BITS>(a, i)] = wn[i];
+          for (int i = 0; i < NR; ++i) w[i] = wn[i];
           if (hl + 1 < nh) {
             const uint32_t* nxt = col + (int64_t)(hl + 1) * W * p.Lmax;
 #pragma unroll
             for (int i = 0; i < NR; ++i) wn[i] = ld_stream_u32(nxt + (int64_t)chunk_row<BITS>(a, i) * p.Lmax, pol_stream);
           }
-          const float2* tb = s_tab + hl * (kHeadDim * N);
-          float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int c = 16 * a + i;
-            const float2 e0 = tb[c * N + code_of<BITS>(w, c)];
-            const float2 e1 = tb[(c + kHalf) * N + code_of<BITS>(w, c + kHalf)];
-            acc0 = fmaf(cs[i].x, e0.x, acc0);
-            acc0 = fmaf(cs[i].y, e0.y, acc0);
-            acc1 = fmaf(cs[i].x, e1.x, acc1);
-            acc1 = fmaf(cs[i].y, e1.y, acc1);
-          }
-          atomicAdd(&s_part[hl * TT + tid], acc0 + acc1);
+          const float part = k_chunk<BITS, a>(w, tab0 + (uint32_t)hl * (kHeadDim * N * 8), cs);
+          atomicAdd(&s_part[hl * TT + tid], part);
         }
-      }
+      });
     }
     __syncthreads();
 
@@ -154,8 +209,9 @@ __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const
       s_part[hl * TT + tid] = 0.f;  // own column: ready for the next tile
       if (live) {
         float* o = p.out + (int64_t)(h0 + hl) * p.out_stride + t;
-        if (p.accumulate) *o = *o + s;
-        else { s *= p.scale; *o = s; }
+        if (p.accumulate) s += *o;   // legacy: mul += S;  sparse: the outlier pre-pass already deposited its part
+        s *= p.scale;
+        *o = s;
       }
       if (p.gmax != nullptr) {
         const float m = warp_max(live ? s : -INFINITY);
@@ -164,6 +220,104 @@ __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const
     }
     __syncthreads();
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Outlier pre-pass (replaces SPMV_ATOMIC_ROPE_BALANCED, quant_cuda_kernel.cu:472-521): thread = token, walks the
+// token's n_out (value, channel) pairs, RoPE evaluated with the reference's own expressions (theta from a 64-entry
+// powf table, cosf/sinf of theta*pos) -- 42 sincos per token instead of the dense path's former 4096.  The row is
+// sorted by channel, so contributions of one head are consecutive: they are summed in a register and written once
+// per head, without atomics (the thread owns column t of the score matrix in this launch).
+// store_all = 1: every head's entry is written (value or 0)  -> initialises the fused score buffer;
+// store_all = 0: only heads with outliers are touched, out += contribution (legacy accumulate semantics).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kOutThreads = 128;
+
+__global__ void __launch_bounds__(kOutThreads) k_outlier_kernel(
+    const float* __restrict__ q, const float* __restrict__ outliers, const int32_t* __restrict__ outlier_idx,
+    float* __restrict__ out, int64_t out_stride, int64_t L, int H, int n_out, float rope_theta, int pos_offset,
+    int store_all) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_q = reinterpret_cast<float*>(smem_raw);            // [H*128]
+  float* s_theta = s_q + H * kHeadDim;                         // [64]
+  float* s_val = s_theta + kHalf;                              // [128][n_out+1]
+  int32_t* s_idx = reinterpret_cast<int32_t*>(s_val + kOutThreads * (n_out + 1));
+  const int tid = threadIdx.x;
+  const int64_t t0 = (int64_t)blockIdx.x * kOutThreads;
+  const int ntok = (int)min((int64_t)kOutThreads, L - t0);
+  for (int i = tid; i < H * kHeadDim; i += kOutThreads) s_q[i] = q[i];
+  if (tid < kHalf) {
+    const int headdim = kHeadDim;
+    s_theta[tid] = powf(rope_theta, (-2 * __int2float_rd(tid % (headdim / 2)) / headdim));  // DK.cu:504
+  }
+  const int total = ntok * n_out;
+  const int stride = n_out + 1;
+  for (int e = tid; e < total; e += kOutThreads) {  // rows [t0, t0+ntok) are contiguous: coalesced
+    const int r = e / n_out, k = e - r * n_out;
+    s_val[r * stride + k] = outliers[t0 * n_out + e];
+    s_idx[r * stride + k] = outlier_idx[t0 * n_out + e];
+  }
+  __syncthreads();
+  if (tid >= ntok) return;
+  const int64_t t = t0 + tid;
+  const int pos = (int)t + pos_offset;
+  float* ocol = out + t;
+  int next_h = 0;       // store_all: next head that still has to be written
+  int cur_h = -1;
+  float acc = 0.f;
+  for (int k = 0; k < n_out; ++k) {
+    const float v = s_val[tid * stride + k];
+    if (v == 0.f) continue;  // pads / non-outliers contribute exactly 0 in the reference too
+    const int col = s_idx[tid * stride + k];
+    const int h = col >> 7, c = col & (kHeadDim - 1);
+    if (h != cur_h) {
+      if (cur_h >= 0) {
+        if (store_all) {
+          for (; next_h < cur_h; ++next_h) ocol[(int64_t)next_h * out_stride] = 0.f;
+          ocol[(int64_t)cur_h * out_stride] = acc;
+          next_h = cur_h + 1;
+        } else {
+          ocol[(int64_t)cur_h * out_stride] += acc;
+        }
+      }
+      cur_h = h;
+      acc = 0.f;
+    }
+    const float theta = s_theta[c & (kHalf - 1)];
+    const float sign = (c < kHalf) ? 1.f : -1.f;
+    const float cs = cosf(theta * pos);
+    const float sn = sinf(theta * pos);
+    float dot = v * cs * s_q[col];
+    dot += sign * v * sn * s_q[col ^ kHalf];
+    acc += dot;
+  }
+  if (cur_h >= 0) {
+    if (store_all) {
+      for (; next_h < cur_h; ++next_h) ocol[(int64_t)next_h * out_stride] = 0.f;
+      ocol[(int64_t)cur_h * out_stride] = acc;
+      next_h = cur_h + 1;
+    } else {
+      ocol[(int64_t)cur_h * out_stride] += acc;
+    }
+  }
+  if (store_all)
+    for (; next_h < H; ++next_h) ocol[(int64_t)next_h * out_stride] = 0.f;
+}
+
+static int launch_k_outliers(const KParams& p, float rope_theta, int store_all, cudaStream_t st) {
+  const size_t smem = (size_t)p.H * kHeadDim * 4 + kHalf * 4 + (size_t)kOutThreads * (p.n_out + 1) * 8;
+  if (smem > 200 * 1024) return KVQ_E_UNSUPPORTED;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_outlier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr = smem;
+  }
+  const unsigned grid = (unsigned)((p.L + kOutThreads - 1) / kOutThreads);
+  k_outlier_kernel<<<grid, kOutThreads, smem, st>>>(p.q, p.outliers, p.outlier_idx, p.out, p.out_stride, p.L, p.H,
+                                                    p.n_out, rope_theta, p.pos_offset, store_all);
+  KVQ_LAUNCH_CHECK();
+  return 0;
 }
 
 // rope table: reference expressions quant_cuda_kernel.cu:3081 (theta) and 3123-3126 (cos/sin), once per (j, p)
@@ -183,7 +337,7 @@ __global__ void rope_table_kernel(float2* __restrict__ out, float rope_theta, in
 template <int BITS>
 static int launch_k_scores(const KParams& p, cudaStream_t st) {
   using C = KCfg<BITS>;
-  const size_t smem = (size_t)C::G * kHeadDim * C::N * sizeof(float2) + (size_t)C::G * kHeadDim * 4 + (size_t)C::G * C::TT * 4;
+  const size_t smem = 256 + (size_t)C::G * kHeadDim * C::N * sizeof(float2) + (size_t)C::G * kHeadDim * 4 + (size_t)C::G * C::TT * 4;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(k_scores_kernel<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -216,13 +370,18 @@ int k_scores_dispatch(int bits, const KParams& p, cudaStream_t st) {
 
 int k_scores_fused(int bits, const float* q, const int32_t* cache, float* scores, int64_t score_stride,
                    const float* lut, const float* outliers, const int32_t* outlier_idx, int n_out, int H,
-                   int64_t Lmax, int64_t L, const float* rope, int64_t rope_npos, int pos_offset, float* gmax,
-                   float scale, cudaStream_t st) {
+                   int64_t Lmax, int64_t L, const float* rope, int64_t rope_npos, float theta, int pos_offset,
+                   float* gmax, float scale, cudaStream_t st) {
   KParams p{};
   p.q = q; p.cache = reinterpret_cast<const uint32_t*>(cache); p.out = scores; p.lut = lut;
   p.outliers = outliers; p.outlier_idx = outlier_idx; p.rope = reinterpret_cast<const float2*>(rope);
   p.gmax = gmax; p.Lmax = Lmax; p.L = L; p.out_stride = score_stride; p.rope_npos = rope_npos;
   p.H = H; p.n_out = n_out; p.pos_offset = pos_offset; p.scale = scale; p.accumulate = 0;
+  if (outliers != nullptr) {
+    const int rc = launch_k_outliers(p, theta, /*store_all=*/1, st);  // initialises the score buffer
+    if (rc != 0) return rc;
+    p.accumulate = 1;
+  }
   return k_scores_dispatch(bits, p, st);
 }
 
@@ -243,7 +402,7 @@ int kvq_rope_table_build(float* rope_cos_sin, float theta, int64_t n_pos, void* 
 
 int kvq_k_matvec(int bits, const float* q, const int32_t* cache, float* mul, const float* lut, int B, int H,
                  int64_t Lmax, int64_t L, const float* outliers, const int32_t* outlier_idx, int n_out,
-                 const float* rope_cos_sin, int64_t rope_npos, int pos_offset, void* stream) {
+                 const float* rope_cos_sin, int64_t rope_npos, float theta, int pos_offset, void* stream) {
   if (!q || !cache || !mul || !lut || !rope_cos_sin) return KVQ_E_NULL;
   if (B <= 0 || H <= 0 || L < 0 || L > Lmax || pos_offset < 0) return KVQ_E_SHAPE;
   if ((outliers == nullptr) != (outlier_idx == nullptr)) return KVQ_E_NULL;
@@ -263,6 +422,10 @@ int kvq_k_matvec(int bits, const float* q, const int32_t* cache, float* mul, con
     p.Lmax = Lmax; p.L = L; p.out_stride = L; p.rope_npos = rope_npos;
     p.H = H; p.n_out = n_out; p.pos_offset = pos_offset;
     p.scale = 1.f; p.accumulate = 1;
+    if (outliers != nullptr) {
+      const int rc0 = launch_k_outliers(p, theta, /*store_all=*/0, static_cast<cudaStream_t>(stream));
+      if (rc0 != 0) return rc0;
+    }
     const int rc = k_scores_dispatch(bits, p, static_cast<cudaStream_t>(stream));
     if (rc != 0) return rc;
   }

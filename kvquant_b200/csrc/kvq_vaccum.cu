@@ -454,8 +454,8 @@ int v_accum_dispatch(int bits, const VParams& p, const int32_t* cache, int* n_ct
 struct KParams;  // kvq_kscore.cu
 int k_scores_fused(int bits, const float* q, const int32_t* cache, float* scores, int64_t score_stride,
                    const float* lut, const float* outliers, const int32_t* outlier_idx, int n_out, int H,
-                   int64_t Lmax, int64_t L, const float* rope, int64_t rope_npos, int pos_offset, float* gmax,
-                   float scale, cudaStream_t st);
+                   int64_t Lmax, int64_t L, const float* rope, int64_t rope_npos, float theta, int pos_offset,
+                   float* gmax, float scale, cudaStream_t st);
 
 static int check_v_common(int H, int64_t Lmax, int64_t L, const void* cache) {
   if (H <= 0 || (H & 3) != 0 || H > 64 || L < 0 || L > Lmax) return KVQ_E_SHAPE;
@@ -505,8 +505,8 @@ int64_t kvq_attend_scratch_bytes(int H, int64_t L) {
 int kvq_attend(int bits, const float* q, const int32_t* kcache, const float* klut, const float* k_outliers,
                const int32_t* k_outlier_idx, const int32_t* vcache, const float* vlut_tok, const float* v_outliers,
                const int32_t* v_outlier_idx, int n_out, int H, int64_t Lmax, int64_t L, const float* rope_cos_sin,
-               int64_t rope_npos, int pos_offset, const void* sink_k, const void* sink_v, int n_sink, float* out,
-               void* scratch, void* stream) {
+               int64_t rope_npos, float theta, int pos_offset, const void* sink_k, const void* sink_v, int n_sink,
+               float* out, void* scratch, void* stream) {
   if (!q || !kcache || !klut || !vcache || !vlut_tok || !rope_cos_sin || !out || !scratch) return KVQ_E_NULL;
   int rc = check_v_common(H, Lmax, L, vcache);
   if (rc) return rc;
@@ -528,7 +528,7 @@ int kvq_attend(int bits, const float* q, const int32_t* kcache, const float* klu
   int n_cta = 0;
   if (L > 0) {
     rc = k_scores_fused(bits, q, kcache, scores, stride, klut, k_outliers, k_outlier_idx, n_out, H, Lmax, L,
-                        rope_cos_sin, rope_npos, pos_offset, gmax, scale, st);
+                        rope_cos_sin, rope_npos, theta, pos_offset, gmax, scale, st);
     if (rc) return rc;
     VParams p{};
     p.score = scores; p.lut_tok = vlut_tok; p.out = part_o; p.out_l = part_l; p.gmax = gmax;

@@ -1,0 +1,224 @@
+"""LLaMA-shaped batch-1 decode harness over the quantised KV cache, and its layer-group pipeline.
+
+The reference drives the hot path from deployment/llama.py:72-94 (token-by-token decode loop) through its forked
+HF LlamaModel; the forked transformers 4.3x does not import under the installed 5.5.0 and there are no weights
+offline, so this is a self-contained decoder with the same per-layer dataflow as
+LlamaFlashAttention2.forward at q_len == 1 (modeling_llama.py:1778-2011):
+
+    v/q/k proj -> RoPE on Q only -> append pre-RoPE K and V (quantise + outlier split) -> Q.K^T over the
+    compressed cache (+ fp16 sinks) -> softmax -> .V -> o_proj -> MLP
+
+with random-init fp16 weights of the LLaMA architecture.  The dense GEMVs are plain library calls (cuBLAS through
+torch); everything that touches the KV cache goes through the C ABI (kvq_append_kv_fused, kvq_attend).
+
+Multi-GPU: the reference's only parallelism is naive layer-group model parallelism
+(`LlamaModel.set_devices`, modeling_llama.py:2428-2453: len(layers)//n_gpus consecutive layers per device, hidden
+state moved with .to(device) at the split points and back to cuda:0 at the end, 2552-2585).  `PipelineDecoder`
+is the one-process-per-GPU form of that: rank r owns layers [r*n/N, (r+1)*n/N) with their full-length caches,
+the [hidden] fp16 vector hops rank r -> r+1 with NCCL send/recv (NVLink P2P), and the last rank returns it to
+rank 0 for norm + lm_head.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+
+from .cache import LayerCache, HEAD_DIM
+
+
+@dataclass
+class DecodeConfig:
+    n_layers: int = 32
+    hidden: int = 4096
+    n_heads: int = 32
+    intermediate: int = 11008
+    vocab: int = 32000
+    rope_theta: float = 10000.0
+    rms_eps: float = 1e-5
+    bits: int = 4
+    n_sink: int = 0            # first_few_fp16
+    sparsity_threshold: float = 0.99
+    include_sparse: bool = True
+    max_len: int = 4096        # quantised slots allocated per layer
+
+    @staticmethod
+    def llama7b(**kw):
+        return DecodeConfig(32, 4096, 32, 11008, 32000, **kw)
+
+    @staticmethod
+    def llama13b(**kw):
+        return DecodeConfig(40, 5120, 40, 13824, 32000, **kw)
+
+
+def partition_layers(n_layers: int, world: int, rank: int):
+    """Layer range of `rank` -- the reference's split rule (modeling_llama.py:2442-2453): n_layers // world
+    consecutive layers per device, the remainder goes to the last device."""
+    per = n_layers // world
+    lo = rank * per
+    hi = n_layers if rank == world - 1 else lo + per
+    return lo, hi
+
+
+def rmsnorm(x, w, eps):
+    xf = x.float()
+    return (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).to(x.dtype) * w
+
+
+class DecoderLayer:
+    def __init__(self, cfg: DecodeConfig, device, gen, quantizer):
+        h, it = cfg.hidden, cfg.intermediate
+        def w(*shape):
+            return (torch.randn(shape, generator=gen, device=device, dtype=torch.float32) * 0.02).half()
+        self.wqkv = w(3 * h, h)
+        self.wo = w(h, h)
+        self.wgu = w(2 * it, h)
+        self.wdown = w(h, it)
+        self.n1 = torch.ones(h, dtype=torch.float16, device=device)
+        self.n2 = torch.ones(h, dtype=torch.float16, device=device)
+        self.cache = LayerCache.from_luts(cfg.bits, cfg.n_heads, cfg.max_len, quantizer["klut"], quantizer["v_cent"],
+                                          device=device, include_sparse=cfg.include_sparse,
+                                          sparsity_threshold=cfg.sparsity_threshold, n_sink=cfg.n_sink)
+        if cfg.n_sink:
+            sk = (torch.randn((cfg.n_heads, HEAD_DIM, cfg.n_sink), generator=gen, device=device)).half()
+            sv = (torch.randn((cfg.n_heads, cfg.n_sink, HEAD_DIM), generator=gen, device=device)).half()
+            self.cache.set_sinks(sk, sv)
+
+
+class DecoderStage:
+    """Layers [lo, hi) of the model on one device, plus (first stage) the embedding and (rank 0) norm + lm_head."""
+
+    def __init__(self, cfg: DecodeConfig, lo: int, hi: int, device, quantizer, seed=0, with_head=True):
+        self.cfg, self.lo, self.hi = cfg, lo, hi
+        self.device = torch.device(device)
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed(seed * 1000 + lo)
+        self.layers = [DecoderLayer(cfg, self.device, gen, quantizer) for _ in range(lo, hi)]
+        self.with_head = with_head
+        if with_head:
+            self.embed = (torch.randn((cfg.vocab, cfg.hidden), generator=gen, device=self.device) * 0.02).half()
+            self.norm = torch.ones(cfg.hidden, dtype=torch.float16, device=self.device)
+            self.lm_head = (torch.randn((cfg.vocab, cfg.hidden), generator=gen, device=self.device) * 0.02).half()
+        half = HEAD_DIM // 2
+        self.inv_freq = 1.0 / (cfg.rope_theta ** (torch.arange(0, HEAD_DIM, 2, device=self.device).float() / HEAD_DIM))
+        self._half = half
+
+    # -- pieces -------------------------------------------------------------------------------------------------
+    def embed_token(self, tok):
+        return self.embed[tok].view(-1)
+
+    def head(self, x):
+        return self.lm_head @ rmsnorm(x, self.norm, self.cfg.rms_eps)
+
+    def _rope_q(self, q, pos):
+        """HF rotate-half RoPE on the query only (modeling_llama.py:1851-1859); q f32 [H,128]."""
+        ang = self.inv_freq * float(pos)
+        cos = torch.cat((ang.cos(), ang.cos()))
+        sin = torch.cat((ang.sin(), ang.sin()))
+        rot = torch.cat((-q[:, self._half:], q[:, :self._half]), dim=-1)
+        return q * cos + rot * sin
+
+    def forward(self, x):
+        """x: fp16 [hidden] -> fp16 [hidden] after this stage's layers; appends one token to every layer cache."""
+        cfg = self.cfg
+        H = cfg.n_heads
+        for ly in self.layers:
+            c = ly.cache
+            pos = c.n_sink + c.len                       # absolute position of the new token
+            qkv = ly.wqkv @ rmsnorm(x, ly.n1, cfg.rms_eps)
+            q, k, v = qkv.float().split(cfg.hidden)
+            q = self._rope_q(q.view(H, HEAD_DIM), pos).contiguous()
+            c.append(k.contiguous(), v.contiguous())     # pre-RoPE K, per-token V: quantise + outlier split
+            o = c.attend(q, rope_theta=cfg.rope_theta)   # f32 [H,128]
+            x = x + ly.wo @ o.half().view(-1)
+            gu = ly.wgu @ rmsnorm(x, ly.n2, cfg.rms_eps)
+            g, u = gu.split(cfg.intermediate)
+            x = x + ly.wdown @ (torch.nn.functional.silu(g) * u)
+        return x
+
+    def set_len(self, L):
+        for ly in self.layers:
+            ly.cache.len = L
+
+    def weight_bytes(self):
+        n = sum(t.numel() * 2 for ly in self.layers for t in (ly.wqkv, ly.wo, ly.wgu, ly.wdown))
+        if self.with_head:
+            n += self.lm_head.numel() * 2
+        return n
+
+
+class GraphedStage:
+    """One decode step of a stage captured in a CUDA graph (the reference's host syncs make that impossible;
+    here nothing in the step touches the host).  The captured step appends at slot L and attends over L+1 slots;
+    replaying it re-runs exactly that step (the fused append overwrites its slot, so replays are idempotent)."""
+
+    def __init__(self, stage: DecoderStage, L: int, first: bool, last_to_logits: bool):
+        self.stage = stage
+        dev = stage.device
+        cfg = stage.cfg
+        self.tok = torch.zeros(1, dtype=torch.long, device=dev)
+        self.x_in = torch.zeros(cfg.hidden, dtype=torch.float16, device=dev)
+        self.first, self.last_to_logits = first, last_to_logits
+
+        def body():
+            x = stage.embed_token(self.tok) if first else self.x_in
+            stage.set_len(L)
+            y = stage.forward(x)
+            return y
+
+        # warm-up on a side stream (allocates scratch, sets func attributes, builds rope tables)
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                y = body()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.y = body()
+            if last_to_logits and stage.with_head:
+                self.logits = stage.head(self.y)
+        stage.set_len(L + 1)
+
+    def replay(self):
+        self.graph.replay()
+
+
+def layer_step_bytes(cfg: DecodeConfig, L: int):
+    """Algorithmic HBM bytes of one layer's fused attend at cache length L."""
+    n_out = 2 * (int(((1 - cfg.sparsity_threshold) / 2) * cfg.hidden) + 1)
+    per_tok = 2 * cfg.hidden * cfg.bits // 8 + 4 * 2 ** cfg.bits + (16 * n_out if cfg.include_sparse else 0)
+    return L * per_tok
+
+
+class PipelineDecoder:
+    """Layer-group pipeline over torch.distributed (one process per GPU; NCCL P2P of the hidden vector).
+    Works with world_size == 1 (no communication) and, for host-logic tests, on the gloo backend with CPU
+    tensors when `stage_fn` is supplied instead of a CUDA stage."""
+
+    def __init__(self, rank, world, hidden, dtype, device, stage_fn, head_fn=None, embed_fn=None, group=None):
+        self.rank, self.world = rank, world
+        self.stage_fn, self.head_fn, self.embed_fn = stage_fn, head_fn, embed_fn
+        self.buf = torch.zeros(hidden, dtype=dtype, device=device)
+        self.group = group
+
+    def step(self, tok):
+        """One decode step.  rank 0: embeds `tok`, runs its layers, sends on; rank r: recv, layers, send;
+        the last rank sends the final hidden state back to rank 0, which applies norm + lm_head.
+        Returns logits on rank 0, None elsewhere."""
+        import torch.distributed as dist
+        w, r = self.world, self.rank
+        if r == 0:
+            x = self.embed_fn(tok)
+        else:
+            dist.recv(self.buf, src=r - 1, group=self.group)
+            x = self.buf
+        y = self.stage_fn(x)
+        if w > 1:
+            dist.send(y.contiguous(), dst=(r + 1) % w, group=self.group)
+            if r == 0:
+                dist.recv(self.buf, src=w - 1, group=self.group)
+                y = self.buf
+        return self.head_fn(y) if r == 0 else None

@@ -160,7 +160,7 @@ def _k_matvec(bits, vec, mat, mul, lookup_table, kcachelen, outliers, outlier_in
         rope, npos = rope_table(mat.device, theta, L + int(pos_offset))
         _lib.check(lib.kvq_k_matvec(bits, _f32(vec, "vec"), _i32(mat, "mat"), _f32(mul, "mul"),
                                     _f32(lookup_table, "lookup_table"), B, H, Lmax, L, po, pi, n_out,
-                                    rope.data_ptr(), npos, int(pos_offset), _stream()), "matmul K")
+                                    rope.data_ptr(), npos, float(theta), int(pos_offset), _stream()), "matmul K")
 
 
 def _v_matvec(bits, vec, mat, mul, lookup_table, vcachelen, outliers, outlier_indices):
