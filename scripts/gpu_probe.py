@@ -85,6 +85,12 @@ def main():
             def run_vd(mod):
                 getattr(mod, vd)(p, lc.vcache, mulV, lc.vlut, L)
 
+            if os.environ.get("PROBE_QUICK"):   # under ncu: just a few launches of each op
+                for _ in range(2):
+                    run_k(qc); run_v(qc)
+                    lc.attend(q[0].contiguous())
+                torch.cuda.synchronize()
+                continue
             # ---- correctness at full size against the reference kernels --------------------------------------
             if ref is not None and L <= 1 << 20:
                 for nm, runner, buf in (("k_opt2", run_k, mulK), ("v_opt2", run_v, mulV), ("k_opt", run_kd, mulK), ("v_opt", run_vd, mulV)):

@@ -12,7 +12,7 @@ if [ "${RUN_BENCH:-1}" = "1" ]; then
   tail -3 gpurun_out/bench.log; tail -5 gpurun_out/bench.err
 fi
 if [ "${RUN_NCU:-1}" = "1" ]; then
-  PROBE_BITS=4 PROBE_L=131072 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_probe.csv python scripts/gpu_probe.py > gpurun_out/ncu_list.log 2>&1
-  PROBE_BITS=4 PROBE_L=131072 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_scores_kernel|v_accum_kernel|k_outlier_kernel' -s 6 -c 6 -o gpurun_out/prof_kv python scripts/gpu_probe.py > gpurun_out/ncu_full.log 2>&1
+  PROBE_QUICK=1 PROBE_BITS=4,3 PROBE_L=131072 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_probe.csv python scripts/gpu_probe.py > gpurun_out/ncu_list.log 2>&1
+  PROBE_QUICK=1 PROBE_BITS=4 PROBE_L=131072 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_scores_kernel|v_accum_kernel|k_outlier_kernel' -s 3 -c 8 -o gpurun_out/prof_kv python scripts/gpu_probe.py > gpurun_out/ncu_full.log 2>&1
   ls -la gpurun_out | tail -12
 fi
