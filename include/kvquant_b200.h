@@ -113,6 +113,9 @@ KVQ_API int kvq_v_matvec(int bits, const float* score, const int32_t* cache, flo
  * Fused decode attention (native op; no single counterpart in the reference -- it is the chain
  * modeling_llama.py:1928-1995: K op -> /sqrt(128) -> [cat sink scores] -> softmax -> V op [+ sink output]).
  *   out[h,:] = softmax_t( S[h,t]/sqrt(128) ) . V      over the L quantised slots and n_sink fp16 sink tokens.
+ * V side: either the reference's materialised per-token LUT (vlut_tok f32 [Lmax,2^bits]) or -- faster -- the
+ * sorted centroids v_cent f32 [2^bits] plus the per-token affine map v_aff f32 [Lmax,2] = (sf_t, off_t) with
+ * LUT_t[i] = v_cent[i]*sf_t + off_t (what kvq_append_kv_fused writes); when both are given the affine form is used.
  * scratch: device buffer of kvq_attend_scratch_bytes(H, L) bytes.
  * sink_k: f16 [H,128,n_sink] post-RoPE keys, sink_v: f16 [H,n_sink,128] (modeling_llama.py:1464-1466), or NULL.
  * out: f32 [H,128].
@@ -121,7 +124,7 @@ KVQ_API int64_t kvq_attend_scratch_bytes(int H, int64_t L);
 KVQ_API int kvq_attend(int bits, const float* q,
                const int32_t* kcache, const float* klut,
                const float* k_outliers, const int32_t* k_outlier_idx,
-               const int32_t* vcache, const float* vlut_tok,
+               const int32_t* vcache, const float* vlut_tok, const float* v_cent, const float* v_aff,
                const float* v_outliers, const int32_t* v_outlier_idx,
                int n_out, int H, int64_t Lmax, int64_t L,
                const float* rope_cos_sin, int64_t rope_npos, float theta, int pos_offset,
@@ -135,14 +138,15 @@ KVQ_API int kvq_attend(int bits, const float* q,
  *   k_new, v_new: f32 [H*128].  n_each = int(((1-t)/2)*hidden)+1 (21 for 7B): K keeps the n_each largest /
  *   smallest normalised values, V thresholds are the (n_each+1)-th order statistics.
  *   klut_sub: LUT used for the K end-entry subtraction (lookup_table2 under Q-Norm), may equal klut.
- *   v_cent: f32 [2^bits] sorted centroids; vlut_tok row `slot` is WRITTEN.
+ *   v_cent: f32 [2^bits] sorted centroids; vlut_tok row `slot` is WRITTEN; v_aff (optional, f32 [Lmax,2]) row
+ *   `slot` receives (sf, off).
  *   Cache words at `slot` are OVERWRITTEN (not added).  Outlier rows (f32/i32 [Lmax, 2*n_each]) row `slot` written.
  * ------------------------------------------------------------------------------------------------------------- */
 KVQ_API int kvq_append_kv_fused(int bits, int H, int64_t Lmax, int64_t slot, int n_each,
                         const float* k_new, int32_t* kcache, const float* klut, const float* klut_sub,
                         const float* k_thr_lower, const float* k_thr_upper,
                         float* k_outliers, int32_t* k_outlier_idx,
-                        const float* v_new, int32_t* vcache, const float* v_cent, float* vlut_tok,
+                        const float* v_new, int32_t* vcache, const float* v_cent, float* vlut_tok, float* v_aff,
                         float* v_outliers, int32_t* v_outlier_idx,
                         void* stream);
 

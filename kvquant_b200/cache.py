@@ -70,6 +70,9 @@ class LayerCache:
         self.thr_lower, self.thr_upper = thr_lower.contiguous(), thr_upper.contiguous()
         self.v_cent = v_cent.contiguous()
         self.vlut = torch.zeros((self.Lmax, 2 ** bits), dtype=torch.float32, device=dev)
+        # per-token affine map (sf_t, off_t): LUT_t = v_cent*sf_t + off_t  -- what the native V kernel consumes
+        self.vaff = torch.zeros((self.Lmax, 2), dtype=torch.float32, device=dev)
+        self.use_native_v = True
         self.k_outliers = torch.zeros((self.Lmax, self.n_out), dtype=torch.float32, device=dev)
         self.k_outlier_idx = torch.zeros((self.Lmax, self.n_out), dtype=torch.int32, device=dev)
         self.v_outliers = torch.zeros((self.Lmax, self.n_out), dtype=torch.float32, device=dev)
@@ -94,8 +97,8 @@ class LayerCache:
 
     def reset(self):
         self.len = 0
-        for x in (self.kcache, self.vcache, self.vlut, self.k_outliers, self.k_outlier_idx, self.v_outliers,
-                  self.v_outlier_idx):
+        for x in (self.kcache, self.vcache, self.vlut, self.vaff, self.k_outliers, self.k_outlier_idx,
+                  self.v_outliers, self.v_outlier_idx):
             x.zero_()
 
     def set_sinks(self, sink_k, sink_v):
@@ -112,6 +115,15 @@ class LayerCache:
         put(self.k_outliers, src.k_out); put(self.k_outlier_idx, src.k_idx)
         put(self.v_outliers, src.v_out); put(self.v_outlier_idx, src.v_idx)
         self.len = int(src.len)
+        self.derive_vaff()
+
+    def derive_vaff(self):
+        """Recover (sf_t, off_t) from materialised LUT rows (caches filled through the legacy per-token-LUT path):
+        sf = (LUT[n-1]-LUT[0])/(cent[n-1]-cent[0]), off = LUT[0]-cent[0]*sf  (agrees with the stored row to ~1 ulp)."""
+        c0, c1 = self.v_cent[0], self.v_cent[-1]
+        sf = (self.vlut[:, -1] - self.vlut[:, 0]) / (c1 - c0)
+        self.vaff[:, 0] = sf
+        self.vaff[:, 1] = self.vlut[:, 0] - c0 * sf
 
     def append(self, k_new, v_new):
         """Quantise + pack + outlier split of one token's K and V, entirely on the device (one launch)."""
@@ -125,7 +137,8 @@ class LayerCache:
             qc._f32(k_new, "k_new"), self.kcache.data_ptr(), self.klut.data_ptr(), self.klut_sub.data_ptr(),
             self.thr_lower.data_ptr(), self.thr_upper.data_ptr(), self.k_outliers.data_ptr(),
             self.k_outlier_idx.data_ptr(), qc._f32(v_new, "v_new"), self.vcache.data_ptr(), self.v_cent.data_ptr(),
-            self.vlut.data_ptr(), self.v_outliers.data_ptr(), self.v_outlier_idx.data_ptr(), s), "kvq_append_kv_fused")
+            self.vlut.data_ptr(), self.vaff.data_ptr(), self.v_outliers.data_ptr(), self.v_outlier_idx.data_ptr(), s),
+            "kvq_append_kv_fused")
         self.len += 1
 
     def attend(self, q, rope_theta=10000.0, out=None):
@@ -143,6 +156,7 @@ class LayerCache:
             self.bits, qc._f32(q, "q"), self.kcache.data_ptr(), self.klut.data_ptr(),
             self.k_outliers.data_ptr() if sp else None, self.k_outlier_idx.data_ptr() if sp else None,
             self.vcache.data_ptr(), self.vlut.data_ptr(),
+            self.v_cent.data_ptr() if self.use_native_v else None, self.vaff.data_ptr() if self.use_native_v else None,
             self.v_outliers.data_ptr() if sp else None, self.v_outlier_idx.data_ptr() if sp else None,
             self.n_out, self.H, self.Lmax, L, rope.data_ptr(), npos, float(rope_theta), self.n_sink,
             self.sink_k.data_ptr() if ns else None, self.sink_v.data_ptr() if ns else None, ns,

@@ -168,6 +168,6 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
 
 // host: build a 2D tensor map over the packed cache viewed as uint32 [rows = H*W, cols = Lmax]
 int make_cache_tensor_map(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
-                          uint32_t box_cols, uint32_t box_rows, bool swizzle128);
+                          uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
 
 }  // namespace kvq

@@ -27,15 +27,9 @@ template <int BITS> struct KCfg {
   static constexpr int G = 128 / N;            // heads per CTA: 8 / 16 / 32 -> table = G*128*N*8 B = 128 KiB
   static constexpr int kThreads = 512;
   static constexpr int TT = kThreads;          // tokens per tile (thread = token)
-  static constexpr int NR = (BITS == 2) ? 2 : 4;  // packed words a thread needs per (head, 16-pair chunk)
+  static constexpr int NRW = (BITS == 3) ? 4 : 2;  // packed words a thread needs per (head, 8-pair chunk)
+  static constexpr int D = (BITS == 4) ? 8 : 4;    // cp.async prefetch distance in (head, chunk) work items
 };
-
-// packed-word rows (within the head) that hold channels [16a,16a+16) and their +64 partners
-template <int BITS> __host__ __device__ constexpr int chunk_row(int a, int i) {
-  if constexpr (BITS == 4) { return (i < 2) ? (2 * a + i) : (8 + 2 * a + (i - 2)); }
-  else if constexpr (BITS == 2) { return (i == 0) ? a : (4 + a); }
-  else { return (i < 2) ? (3 * (a >> 1) + (a & 1) + i) : (3 * ((a >> 1) + 2) + (a & 1) + (i - 2)); }
-}
 
 struct KParams {
   const float* q;            // [H,128]
@@ -71,89 +65,91 @@ __device__ __forceinline__ void ffma2(float2& acc, const float2 a, const float2 
       " fma.rn.f32x2 rc, ra, rb, rc; mov.b64 {%0,%1}, rc; }"
       : "+f"(acc.x), "+f"(acc.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
 }
+// 4-byte asynchronous global->shared copy (LDGSTS) with an L2 eviction policy; per-thread software pipeline
+__device__ __forceinline__ void cp_async4(uint32_t smem_dst, const void* gsrc, uint64_t pol, int pred) {
+  asm volatile("{ .reg .pred p; setp.ne.s32 p, %3, 0;"
+               " @p cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2; }"
+               ::"r"(smem_dst), "l"(gsrc), "l"(pol), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 
-// One (head, 16-pair chunk A): 32 table lookups + 32 packed FMAs.  `base` = shared address of the head's table
-// (256-byte aligned, so a code*8 byte can be PRMT-ed / OR-ed into its low byte); channel offsets are immediates.
-//   4-bit / 2-bit: the codes of a word are pre-masked into byte lanes (4 resp. 8 logic ops per word), then ONE
-//                  PRMT per element builds the address           -> PRMT + LDS.64 + FFMA2 per element;
-//   3-bit:         one funnel shift + one LOP3 (and-or) per element (straddling codes come for free from the
-//                  funnel shift)                                  -> SHF + LOP3 + LDS.64 + FFMA2 per element.
-template <int BITS, int A>
-__device__ __forceinline__ float k_chunk(const uint32_t* __restrict__ wn, const uint32_t base, const float2* __restrict__ cs) {
+// packed-word rows (relative to the head) needed for 8-pair chunk a (pairs 8a..8a+7): channels 8a..8a+7 and +64
+template <int BITS> __device__ __forceinline__ int chunk_word_row(int a, int i) {
+  if constexpr (BITS == 4) { return i == 0 ? a : a + 8; }
+  else if constexpr (BITS == 2) { return i == 0 ? (a >> 1) : 4 + (a >> 1); }
+  else {
+    // 24-bit window at bit 24*(a&3) of the 96-bit group a>>2 (words 3g..3g+2); i=0/1 low pair of words, i=2/3 high (+2 groups)
+    const int first = (24 * (a & 3)) >> 5;            // 0,0,1,2
+    const int w = (i & 1) ? min(first + 1, 2) : first;
+    return 3 * ((a >> 2) + ((i >> 1) ? 2 : 0)) + w;
+  }
+}
+
+// One work item = (head hl, 8-pair chunk a): 16 table lookups + 16 packed FMAs into the head's accumulator.
+//   base = shared address of T[hl][8a][0] (256-byte aligned: the low address byte carries code*8);
+//   4-bit / 2-bit: codes pre-masked into byte lanes, ONE PRMT per element builds the address;
+//   3-bit: one shift + one LOP3 (and-or) per element on the funnel-shifted 24-bit window.
+template <int BITS>
+__device__ __forceinline__ void k_item(const uint32_t* __restrict__ w, const int a, const uint32_t base,
+                                       const float2* __restrict__ cs, float2& acc) {
   constexpr int N = 1 << BITS;
-  float2 acc[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  constexpr int HI = kHalf * N * 8;  // byte offset of the +64 partner channel's table
   if constexpr (BITS == 4) {
-    // wn[0..1]: channels 16A..16A+15, wn[2..3]: +64
-    static_for<0, 4>([&](auto iw) {
-      constexpr int wi = decltype(iw)::v;
-      constexpr int c0 = 16 * A + (wi & 1) * 8 + (wi >> 1) * kHalf;
-      const uint32_t e = (wn[wi] << 3) & 0x78787878u, o = (wn[wi] >> 1) & 0x78787878u;
-      static_for<0, 8>([&](auto ik) {
-        constexpr int k = decltype(ik)::v;
-        const uint32_t addr = __byte_perm((k & 1) ? o : e, base, 0x7650 | (k >> 1));
-        ffma2(acc[(wi >> 1) * 2 + (k & 1)], cs[(wi & 1) * 8 + k], lds_f2<(c0 + k) * N * 8>(addr));
-      });
+    const uint32_t e0 = (w[0] << 3) & 0x78787878u, o0 = (w[0] >> 1) & 0x78787878u;
+    const uint32_t e1 = (w[1] << 3) & 0x78787878u, o1 = (w[1] >> 1) & 0x78787878u;
+    static_for<0, 8>([&](auto ik) {
+      constexpr int k = decltype(ik)::v;
+      ffma2(acc, cs[k], lds_f2<k * N * 8>(__byte_perm((k & 1) ? o0 : e0, base, 0x7650 | (k >> 1))));
+      ffma2(acc, cs[k], lds_f2<k * N * 8 + HI>(__byte_perm((k & 1) ? o1 : e1, base, 0x7650 | (k >> 1))));
     });
   } else if constexpr (BITS == 2) {
-    // wn[0]: channels 16A..16A+15, wn[1]: +64
-    static_for<0, 2>([&](auto iw) {
-      constexpr int wi = decltype(iw)::v;
-      constexpr int c0 = 16 * A + wi * kHalf;
-      const uint32_t m0 = (wn[wi] << 3) & 0x18181818u, m1 = (wn[wi] << 1) & 0x18181818u;
-      const uint32_t m2 = (wn[wi] >> 1) & 0x18181818u, m3 = (wn[wi] >> 3) & 0x18181818u;
-      static_for<0, 16>([&](auto ik) {
-        constexpr int k = decltype(ik)::v;
-        const uint32_t src = (k & 3) == 0 ? m0 : ((k & 3) == 1 ? m1 : ((k & 3) == 2 ? m2 : m3));
-        const uint32_t addr = __byte_perm(src, base, 0x7650 | (k >> 2));
-        ffma2(acc[wi * 2 + (k & 1)], cs[k], lds_f2<(c0 + k) * N * 8>(addr));
-      });
+    const int sh = 16 * (a & 1);
+    const uint32_t x0 = w[0] >> sh, x1 = w[1] >> sh;
+    const uint32_t m00 = (x0 << 3) & 0x1818u, m01 = (x0 << 1) & 0x1818u, m02 = (x0 >> 1) & 0x1818u, m03 = (x0 >> 3) & 0x1818u;
+    const uint32_t m10 = (x1 << 3) & 0x1818u, m11 = (x1 << 1) & 0x1818u, m12 = (x1 >> 1) & 0x1818u, m13 = (x1 >> 3) & 0x1818u;
+    static_for<0, 8>([&](auto ik) {
+      constexpr int k = decltype(ik)::v;
+      const uint32_t s0 = (k & 3) == 0 ? m00 : ((k & 3) == 1 ? m01 : ((k & 3) == 2 ? m02 : m03));
+      const uint32_t s1 = (k & 3) == 0 ? m10 : ((k & 3) == 1 ? m11 : ((k & 3) == 2 ? m12 : m13));
+      ffma2(acc, cs[k], lds_f2<k * N * 8>(__byte_perm(s0, base, 0x7650 | (k >> 2))));
+      ffma2(acc, cs[k], lds_f2<k * N * 8 + HI>(__byte_perm(s1, base, 0x7650 | (k >> 2))));
     });
   } else {
-    // wn[0..1]: the two words holding locs [16*(A&1), +16) of group A>>1; wn[2..3]: same for group (A>>1)+2
-    static_for<0, 2>([&](auto ih) {
-      constexpr int hf = decltype(ih)::v;
-      const uint32_t w0 = wn[2 * hf], w1 = wn[2 * hf + 1];
-      static_for<0, 16>([&](auto ik) {
-        constexpr int k = decltype(ik)::v;
-        constexpr int l = 16 * (A & 1) + k;               // position within the 32-channel group
-        constexpr int bitpos = 3 * l - 32 * ((A & 1) ? 1 : 0);  // bit offset relative to w0 (may be negative / >= 32)
-        constexpr int c = 16 * A + k + hf * kHalf;
-        uint32_t x;
-        if constexpr (bitpos < 0) {
-          // (A&1)==1 and the code starts in the previous word: cannot happen for l >= 16 (3*16 = 48 >= 32)
-          x = 0;
-        } else if constexpr (bitpos + 3 <= 32) {
-          x = (bitpos >= 3) ? (w0 >> (bitpos - 3)) : (w0 << (3 - bitpos));
-        } else if constexpr (bitpos < 32) {
-          x = __funnelshift_r(w0, w1, bitpos - 3);       // straddles w0 / w1
-        } else {
-          x = (bitpos - 32 >= 3) ? (w1 >> (bitpos - 32 - 3)) : (w1 << (3 - (bitpos - 32)));
-        }
-        const uint32_t addr = (x & 0x38u) | base;
-        ffma2(acc[hf * 2 + (k & 1)], cs[k], lds_f2<c * N * 8>(addr));
-      });
+    const int sh = (24 * (a & 3)) & 31;  // 0, 24, 16, 8
+    const uint32_t x0 = __funnelshift_r(w[0], w[1], sh), x1 = __funnelshift_r(w[2], w[3], sh);
+    static_for<0, 8>([&](auto ik) {
+      constexpr int k = decltype(ik)::v;
+      const uint32_t a0 = ((k == 0 ? (x0 << 3) : (x0 >> (3 * k - 3))) & 0x38u) | base;
+      const uint32_t a1 = ((k == 0 ? (x1 << 3) : (x1 >> (3 * k - 3))) & 0x38u) | base;
+      ffma2(acc, cs[k], lds_f2<k * N * 8>(a0));
+      ffma2(acc, cs[k], lds_f2<k * N * 8 + HI>(a1));
     });
   }
-  return (acc[0].x + acc[0].y) + (acc[1].x + acc[1].y) + (acc[2].x + acc[2].y) + (acc[3].x + acc[3].y);
 }
 
 template <int BITS>
 __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const KParams p) {
   using C = KCfg<BITS>;
-  constexpr int N = C::N, W = C::W, G = C::G, TT = C::TT, NR = C::NR;
+  constexpr int N = C::N, W = C::W, G = C::G, TT = C::TT, NRW = C::NRW, D = C::D;
   extern __shared__ unsigned char smem_raw[];
   // table base must be 256-byte aligned (the low address byte carries code*8)
   unsigned char* smem = smem_raw + ((256u - (smem_u32(smem_raw) & 255u)) & 255u);
-  float2* s_tab = reinterpret_cast<float2*>(smem);                 // [G][128][N]
-  float* s_q = reinterpret_cast<float*>(s_tab + G * kHeadDim * N);  // [G][128]
-  float* s_part = s_q + G * kHeadDim;                              // [G][TT]
+  float2* s_tab = reinterpret_cast<float2*>(smem);                  // [G][128][N]
+  float* s_q = reinterpret_cast<float*>(s_tab + G * kHeadDim * N);   // [G][128]
+  uint32_t* s_ring = reinterpret_cast<uint32_t*>(s_q + G * kHeadDim);  // [D][NRW][TT]
 
   const int tid = threadIdx.x;
   const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
   const int h0 = blockIdx.y * G;
   const int nh = min(G, p.H - h0);
 
-  // ---- premultiplied tables -------------------------------------------------------------------------------
+  // ---- premultiplied tables T[hl][c][code] = (LUT*q[c], s_c*LUT*q[c^64]) -----------------------------------------
   for (int i = tid; i < nh * kHeadDim; i += C::kThreads) s_q[i] = p.q[(int64_t)h0 * kHeadDim + i];
   __syncthreads();
   for (int i = tid; i < nh * kHeadDim * N; i += C::kThreads) {
@@ -164,62 +160,103 @@ __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const
     const float qb = s_q[hc ^ kHalf];  // (c+64)%128 within the same head
     s_tab[i] = make_float2(l * qa, (c < kHalf) ? (l * qb) : -(l * qb));
   }
-  for (int i = tid; i < G * TT; i += C::kThreads) s_part[i] = 0.f;
   __syncthreads();
   const uint32_t tab0 = smem_u32(s_tab);
+  const uint32_t ring0 = smem_u32(s_ring) + tid * 4;
 
-  const int64_t tile0 = (int64_t)blockIdx.x * p.tiles_per_cta;
-  for (int ti = 0; ti < p.tiles_per_cta; ++ti) {
-    const int64_t tbase = (tile0 + ti) * TT;
-    if (tbase >= p.L) break;
-    const int64_t t = tbase + tid;
+  // The CTA walks `tiles_per_cta` tiles of TT tokens; a thread's work items are linearised as
+  // (tile, chunk a = 0..7, head hl = 0..G-1) and the packed words of item i+D are fetched while item i computes.
+  const int64_t tile_first = (int64_t)blockIdx.x * p.tiles_per_cta;
+  const int64_t tile_end = min(tile_first + p.tiles_per_cta, (p.L + TT - 1) / TT);
+  const int64_t t_limit = min(p.L, tile_end * TT);   // tokens this CTA may touch
+  const uint32_t* cbase = p.cache + (int64_t)h0 * W * p.Lmax;
+
+  // issue the copies of item (a, hl) of the current (nxt = 0) or next (nxt = 1) tile into ring slot `slot`, then commit
+  // (always exactly one group per item, so wait_group<D-1> means "the oldest outstanding item has landed").
+  // Row pitch in bytes fits 32 bits (host checks Lmax < 2^30); byte offsets are formed with one IMAD.WIDE per copy.
+  const uint32_t pitch = (uint32_t)p.Lmax * 4u;
+  const unsigned char* cb0 = reinterpret_cast<const unsigned char*>(cbase);
+  int64_t t_cur = tile_first * TT + tid;
+  auto prefetch = [&](int nxt, int a, int hl, int slot) {
+    const int64_t t = t_cur + (nxt ? TT : 0);
+    const int ok = (t < t_limit) && (hl < nh);
+    const unsigned char* src = cb0 + t * 4;
+#pragma unroll
+    for (int i = 0; i < NRW; ++i)
+      cp_async4(ring0 + (uint32_t)(slot * NRW + i) * (TT * 4),
+                src + (uint64_t)(uint32_t)(hl * W + chunk_word_row<BITS>(a, i)) * pitch, pol_stream, ok);
+    cp_async_commit();
+  };
+  auto load_cs = [&](float2* dst, int64_t tile, int a) {
+    const int64_t t = tile * TT + tid;
+    if (t < t_limit) {
+      const float2* rp = p.rope + (t + p.pos_offset) + (int64_t)(8 * a) * p.rope_npos;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dst[k] = ld_keep_f2(rp + (int64_t)k * p.rope_npos, pol_keep);
+    }
+  };
+
+  // prologue: first D items of the first tile, rope values of its first chunk
+  static_for<0, D>([&](auto id) {
+    constexpr int d = decltype(id)::v;
+    prefetch((d / G) / 8, (d / G) % 8, d % G, d % D);
+  });
+  float2 cs[8], csn[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { cs[k] = make_float2(0.f, 0.f); csn[k] = make_float2(0.f, 0.f); }
+  load_cs(cs, tile_first, 0);
+
+  for (int64_t tile = tile_first; tile < tile_end; ++tile) {
+    const int64_t t = tile * TT + tid;
+    t_cur = t;
     const bool live = t < p.L;
+    float2 acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = make_float2(0.f, 0.f);
 
-    // ---- dense part ---------------------------------------------------------------------------------------
-    if (live) {
-      const uint32_t* col = p.cache + (int64_t)h0 * W * p.Lmax + t;
-      const float2* rp = p.rope + (t + p.pos_offset);
-      static_for<0, 4>([&](auto ia) {
-        constexpr int a = decltype(ia)::v;
-        float2 cs[16];
+    for (int a = 0; a < 8; ++a) {
+      // rope values of the next chunk (next tile's chunk 0 after the last one) travel while this chunk computes
+      load_cs(csn, a == 7 ? tile + 1 : tile, (a + 1) & 7);
+      static_for<0, G>([&](auto ig) {
+        constexpr int hl = decltype(ig)::v;
+        cp_async_wait<D - 1>();  // this item's words have landed (one commit group per item)
+        uint32_t w[NRW];
+        constexpr int slot = hl % D;   // G is a multiple of D, so item i lives in slot hl % D
 #pragma unroll
-        for (int i = 0; i < 16; ++i) cs[i] = ld_keep_f2(rp + (int64_t)(16 * a + i) * p.rope_npos, pol_keep);
-        uint32_t wn[NR];
-#pragma unroll
-        for (int i = 0; i < NR; ++i) wn[i] = ld_stream_u32(col + (int64_t)chunk_row<BITS>(a, i) * p.Lmax, pol_stream);
-        for (int hl = 0; hl < nh; ++hl) {
-          uint32_t w[NR];
-#pragma unroll
-          for (int i = 0; i < NR; ++i) w[i] = wn[i];
-          if (hl + 1 < nh) {
-            const uint32_t* nxt = col + (int64_t)(hl + 1) * W * p.Lmax;
-#pragma unroll
-            for (int i = 0; i < NR; ++i) wn[i] = ld_stream_u32(nxt + (int64_t)chunk_row<BITS>(a, i) * p.Lmax, pol_stream);
-          }
-          const float part = k_chunk<BITS, a>(w, tab0 + (uint32_t)hl * (kHeadDim * N * 8), cs);
-          atomicAdd(&s_part[hl * TT + tid], part);
+        for (int i = 0; i < NRW; ++i) w[i] = lds_u32(ring0 + (uint32_t)(slot * NRW + i) * (TT * 4));
+        // item i+D re-uses this slot: its copies are issued only after w[] has been read into registers
+        // (lds_u32 is volatile and precedes the copy in program order; the words are consumed below)
+        {
+          constexpr int hn = (hl + D) % G;
+          constexpr int wrap = (hl + D) / G;  // 0 or 1: next chunk
+          const int an = a + wrap;
+          prefetch(an >> 3, an & 7, hn, slot);
         }
+        if (live && hl < nh) k_item<BITS>(w, a, tab0 + (uint32_t)hl * (kHeadDim * N * 8) + (uint32_t)a * (8 * N * 8), cs, acc[hl]);
       });
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cs[k] = csn[k];
     }
-    __syncthreads();
 
-    // ---- write back -----------------------------------------------------------------------------------------
-    for (int hl = 0; hl < nh; ++hl) {
-      float s = s_part[hl * TT + tid];
-      s_part[hl * TT + tid] = 0.f;  // own column: ready for the next tile
-      if (live) {
-        float* o = p.out + (int64_t)(h0 + hl) * p.out_stride + t;
-        if (p.accumulate) s += *o;   // legacy: mul += S;  sparse: the outlier pre-pass already deposited its part
-        s *= p.scale;
-        *o = s;
-      }
-      if (p.gmax != nullptr) {
-        const float m = warp_max(live ? s : -INFINITY);
-        if ((tid & 31) == 0 && m > -INFINITY) atomic_max_float(p.gmax + h0 + hl, m);
+    // ---- write back: this thread owns column t of the score matrix for the CTA's heads ---------------------------
+#pragma unroll
+    for (int hl = 0; hl < G; ++hl) {
+      if (hl < nh) {
+        float s = acc[hl].x + acc[hl].y;
+        if (live) {
+          float* o = p.out + (int64_t)(h0 + hl) * p.out_stride + t;
+          if (p.accumulate) s += *o;   // legacy: mul += S;  sparse: the outlier pre-pass already deposited its part
+          s *= p.scale;
+          *o = s;
+        }
+        if (p.gmax != nullptr) {
+          const float m = warp_max(live ? s : -INFINITY);
+          if ((tid & 31) == 0 && m > -INFINITY) atomic_max_float(p.gmax + h0 + hl, m);
+        }
       }
     }
-    __syncthreads();
   }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -231,7 +268,8 @@ __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const
 // store_all = 1: every head's entry is written (value or 0)  -> initialises the fused score buffer;
 // store_all = 0: only heads with outliers are touched, out += contribution (legacy accumulate semantics).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kOutThreads = 128;
+constexpr int kOutThreads = 256;
+constexpr int kOutBatch = 6;   // (value, index) pairs fetched per thread before they are consumed
 
 __global__ void __launch_bounds__(kOutThreads) k_outlier_kernel(
     const float* __restrict__ q, const float* __restrict__ outliers, const int32_t* __restrict__ outlier_idx,
@@ -240,79 +278,65 @@ __global__ void __launch_bounds__(kOutThreads) k_outlier_kernel(
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_q = reinterpret_cast<float*>(smem_raw);            // [H*128]
   float* s_theta = s_q + H * kHeadDim;                         // [64]
-  float* s_val = s_theta + kHalf;                              // [128][n_out+1]
-  int32_t* s_idx = reinterpret_cast<int32_t*>(s_val + kOutThreads * (n_out + 1));
   const int tid = threadIdx.x;
-  const int64_t t0 = (int64_t)blockIdx.x * kOutThreads;
-  const int ntok = (int)min((int64_t)kOutThreads, L - t0);
   for (int i = tid; i < H * kHeadDim; i += kOutThreads) s_q[i] = q[i];
   if (tid < kHalf) {
     const int headdim = kHeadDim;
     s_theta[tid] = powf(rope_theta, (-2 * __int2float_rd(tid % (headdim / 2)) / headdim));  // DK.cu:504
   }
-  const int total = ntok * n_out;
-  const int stride = n_out + 1;
-  for (int e = tid; e < total; e += kOutThreads) {  // rows [t0, t0+ntok) are contiguous: coalesced
-    const int r = e / n_out, k = e - r * n_out;
-    s_val[r * stride + k] = outliers[t0 * n_out + e];
-    s_idx[r * stride + k] = outlier_idx[t0 * n_out + e];
-  }
   __syncthreads();
-  if (tid >= ntok) return;
-  const int64_t t = t0 + tid;
+  const int64_t t = (int64_t)blockIdx.x * kOutThreads + tid;
+  if (t >= L) return;
   const int pos = (int)t + pos_offset;
+  const float* vrow = outliers + t * n_out;     // the thread reads its own 2 x n_out x 4 bytes; every fetched sector
+  const int32_t* irow = outlier_idx + t * n_out;  // is consumed completely (L1 keeps it between the batches)
   float* ocol = out + t;
   int next_h = 0;       // store_all: next head that still has to be written
   int cur_h = -1;
   float acc = 0.f;
-  for (int k = 0; k < n_out; ++k) {
-    const float v = s_val[tid * stride + k];
-    if (v == 0.f) continue;  // pads / non-outliers contribute exactly 0 in the reference too
-    const int col = s_idx[tid * stride + k];
-    const int h = col >> 7, c = col & (kHeadDim - 1);
-    if (h != cur_h) {
-      if (cur_h >= 0) {
-        if (store_all) {
-          for (; next_h < cur_h; ++next_h) ocol[(int64_t)next_h * out_stride] = 0.f;
-          ocol[(int64_t)cur_h * out_stride] = acc;
-          next_h = cur_h + 1;
-        } else {
-          ocol[(int64_t)cur_h * out_stride] += acc;
-        }
+  auto flush = [&]() {
+    if (cur_h >= 0) {
+      if (store_all) {
+        for (; next_h < cur_h; ++next_h) ocol[(int64_t)next_h * out_stride] = 0.f;
+        ocol[(int64_t)cur_h * out_stride] = acc;
+        next_h = cur_h + 1;
+      } else {
+        ocol[(int64_t)cur_h * out_stride] += acc;
       }
-      cur_h = h;
-      acc = 0.f;
     }
-    const float theta = s_theta[c & (kHalf - 1)];
-    const float sign = (c < kHalf) ? 1.f : -1.f;
-    const float cs = cosf(theta * pos);
-    const float sn = sinf(theta * pos);
-    float dot = v * cs * s_q[col];
-    dot += sign * v * sn * s_q[col ^ kHalf];
-    acc += dot;
-  }
-  if (cur_h >= 0) {
-    if (store_all) {
-      for (; next_h < cur_h; ++next_h) ocol[(int64_t)next_h * out_stride] = 0.f;
-      ocol[(int64_t)cur_h * out_stride] = acc;
-      next_h = cur_h + 1;
-    } else {
-      ocol[(int64_t)cur_h * out_stride] += acc;
+  };
+  for (int k0 = 0; k0 < n_out; k0 += kOutBatch) {
+    float v[kOutBatch];
+    int ci[kOutBatch];
+#pragma unroll
+    for (int u = 0; u < kOutBatch; ++u) {
+      const bool in = k0 + u < n_out;
+      v[u] = in ? __ldg(vrow + k0 + u) : 0.f;
+      ci[u] = in ? __ldg(irow + k0 + u) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < kOutBatch; ++u) {
+      if (v[u] == 0.f) continue;  // pads / non-outliers contribute exactly 0 in the reference too
+      const int col = ci[u];
+      const int h = col >> 7, c = col & (kHeadDim - 1);
+      if (h != cur_h) { flush(); cur_h = h; acc = 0.f; }
+      const float theta = s_theta[c & (kHalf - 1)];
+      const float sign = (c < kHalf) ? 1.f : -1.f;
+      float sn, cs;
+      sincosf(theta * pos, &sn, &cs);           // same libdevice range reduction as the reference's cosf / sinf
+      float dot = v[u] * cs * s_q[col];
+      dot += sign * v[u] * sn * s_q[col ^ kHalf];
+      acc += dot;
     }
   }
+  flush();
   if (store_all)
     for (; next_h < H; ++next_h) ocol[(int64_t)next_h * out_stride] = 0.f;
 }
 
 static int launch_k_outliers(const KParams& p, float rope_theta, int store_all, cudaStream_t st) {
-  const size_t smem = (size_t)p.H * kHeadDim * 4 + kHalf * 4 + (size_t)kOutThreads * (p.n_out + 1) * 8;
-  if (smem > 200 * 1024) return KVQ_E_UNSUPPORTED;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_outlier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    attr = smem;
-  }
+  const size_t smem = (size_t)p.H * kHeadDim * 4 + kHalf * 4;
+  if (smem > 48 * 1024) return KVQ_E_UNSUPPORTED;
   const unsigned grid = (unsigned)((p.L + kOutThreads - 1) / kOutThreads);
   k_outlier_kernel<<<grid, kOutThreads, smem, st>>>(p.q, p.outliers, p.outlier_idx, p.out, p.out_stride, p.L, p.H,
                                                     p.n_out, rope_theta, p.pos_offset, store_all);
@@ -337,7 +361,7 @@ __global__ void rope_table_kernel(float2* __restrict__ out, float rope_theta, in
 template <int BITS>
 static int launch_k_scores(const KParams& p, cudaStream_t st) {
   using C = KCfg<BITS>;
-  const size_t smem = 256 + (size_t)C::G * kHeadDim * C::N * sizeof(float2) + (size_t)C::G * kHeadDim * 4 + (size_t)C::G * C::TT * 4;
+  const size_t smem = 256 + (size_t)C::G * kHeadDim * C::N * sizeof(float2) + (size_t)C::G * kHeadDim * 4 + (size_t)C::D * C::NRW * C::TT * 4;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(k_scores_kernel<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -404,7 +428,7 @@ int kvq_k_matvec(int bits, const float* q, const int32_t* cache, float* mul, con
                  int64_t Lmax, int64_t L, const float* outliers, const int32_t* outlier_idx, int n_out,
                  const float* rope_cos_sin, int64_t rope_npos, float theta, int pos_offset, void* stream) {
   if (!q || !cache || !mul || !lut || !rope_cos_sin) return KVQ_E_NULL;
-  if (B <= 0 || H <= 0 || L < 0 || L > Lmax || pos_offset < 0) return KVQ_E_SHAPE;
+  if (B <= 0 || H <= 0 || L < 0 || L > Lmax || pos_offset < 0 || Lmax >= ((int64_t)1 << 30)) return KVQ_E_SHAPE;
   if ((outliers == nullptr) != (outlier_idx == nullptr)) return KVQ_E_NULL;
   if (outliers && (B != 1 || n_out <= 0)) return KVQ_E_SHAPE;  // reference: sparse part is batch-1 only (DK.cu:3605)
   if (rope_npos < L + pos_offset) return KVQ_E_SHAPE;

@@ -376,7 +376,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int make_cache_tensor_map(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols,
-                          uint32_t box_rows, bool swizzle128) {
+                          uint32_t box_rows, int swizzle_bytes) {
   static PFN_encodeTiled fn = nullptr;
   if (!fn) {
     // resolve the driver entry point directly (no link-time dependency on libcuda; the library must load on
@@ -392,13 +392,16 @@ int make_cache_tensor_map(CUtensorMap* out, const void* base, uint64_t rows, uin
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
 static int g_sms = 0;
-static int num_sms() {
+int num_sms_cached();
+static int num_sms() { return num_sms_cached(); }
+int num_sms_cached() {
   if (!g_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -430,7 +433,7 @@ static int launch_v(VParams p, const int32_t* cache, int* n_cta_out, cudaStream_
     attr_done = true;
   }
   CUtensorMap tmap;
-  int rc = make_cache_tensor_map(&tmap, cache, (uint64_t)rows, (uint64_t)p.Lmax, kVT, 32, true);
+  int rc = make_cache_tensor_map(&tmap, cache, (uint64_t)rows, (uint64_t)p.Lmax, kVT, 32, 128);
   if (rc != 0) return rc;
   const int64_t n_tiles = (p.L + kVT - 1) / kVT;
   const int sms = num_sms();
@@ -456,6 +459,11 @@ int k_scores_fused(int bits, const float* q, const int32_t* cache, float* scores
                    const float* lut, const float* outliers, const int32_t* outlier_idx, int n_out, int H,
                    int64_t Lmax, int64_t L, const float* rope, int64_t rope_npos, float theta, int pos_offset,
                    float* gmax, float scale, cudaStream_t st);
+
+int v_native_dispatch(int bits, const float* score, int64_t score_stride, const float* gmax, const int32_t* cache,
+                      const float* v_cent, const float* v_aff, const float* outliers, const int32_t* outlier_idx,
+                      int n_out, int H, int64_t Lmax, int64_t L, float* out_o, float* out_l, int* n_cta,
+                      cudaStream_t st);
 
 static int check_v_common(int H, int64_t Lmax, int64_t L, const void* cache) {
   if (H <= 0 || (H & 3) != 0 || H > 64 || L < 0 || L > Lmax) return KVQ_E_SHAPE;
@@ -503,17 +511,19 @@ int64_t kvq_attend_scratch_bytes(int H, int64_t L) {
 }
 
 int kvq_attend(int bits, const float* q, const int32_t* kcache, const float* klut, const float* k_outliers,
-               const int32_t* k_outlier_idx, const int32_t* vcache, const float* vlut_tok, const float* v_outliers,
-               const int32_t* v_outlier_idx, int n_out, int H, int64_t Lmax, int64_t L, const float* rope_cos_sin,
+               const int32_t* k_outlier_idx, const int32_t* vcache, const float* vlut_tok, const float* v_cent,
+               const float* v_aff, const float* v_outliers, const int32_t* v_outlier_idx, int n_out, int H, int64_t Lmax, int64_t L, const float* rope_cos_sin,
                int64_t rope_npos, float theta, int pos_offset, const void* sink_k, const void* sink_v, int n_sink,
                float* out, void* scratch, void* stream) {
-  if (!q || !kcache || !klut || !vcache || !vlut_tok || !rope_cos_sin || !out || !scratch) return KVQ_E_NULL;
+  if (!q || !kcache || !klut || !vcache || !rope_cos_sin || !out || !scratch) return KVQ_E_NULL;
+  const bool native_v = (v_cent != nullptr && v_aff != nullptr);
+  if (!native_v && !vlut_tok) return KVQ_E_NULL;
   int rc = check_v_common(H, Lmax, L, vcache);
   if (rc) return rc;
   if ((k_outliers == nullptr) != (k_outlier_idx == nullptr) || (v_outliers == nullptr) != (v_outlier_idx == nullptr)) return KVQ_E_NULL;
   if ((k_outliers || v_outliers) && n_out <= 0) return KVQ_E_SHAPE;
   if (n_sink < 0 || n_sink > 64 || (n_sink > 0 && (!sink_k || !sink_v))) return KVQ_E_SHAPE;
-  if (L + n_sink == 0 || rope_npos < L + pos_offset) return KVQ_E_SHAPE;
+  if (L + n_sink == 0 || rope_npos < L + pos_offset || Lmax >= ((int64_t)1 << 30)) return KVQ_E_SHAPE;
   if (num_sms() > kMaxPart) return KVQ_E_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t stride = round_up(L, 32);
@@ -530,11 +540,16 @@ int kvq_attend(int bits, const float* q, const int32_t* kcache, const float* klu
     rc = k_scores_fused(bits, q, kcache, scores, stride, klut, k_outliers, k_outlier_idx, n_out, H, Lmax, L,
                         rope_cos_sin, rope_npos, theta, pos_offset, gmax, scale, st);
     if (rc) return rc;
-    VParams p{};
-    p.score = scores; p.lut_tok = vlut_tok; p.out = part_o; p.out_l = part_l; p.gmax = gmax;
-    p.outliers = v_outliers; p.outlier_idx = v_outlier_idx;
-    p.Lmax = Lmax; p.L = L; p.score_stride = stride; p.H = H; p.n_out = n_out; p.fused = 1;
-    rc = v_accum_dispatch(bits, p, vcache, &n_cta, st);
+    if (native_v) {
+      rc = v_native_dispatch(bits, scores, stride, gmax, vcache, v_cent, v_aff, v_outliers, v_outlier_idx, n_out, H,
+                             Lmax, L, part_o, part_l, &n_cta, st);
+    } else {
+      VParams p{};
+      p.score = scores; p.lut_tok = vlut_tok; p.out = part_o; p.out_l = part_l; p.gmax = gmax;
+      p.outliers = v_outliers; p.outlier_idx = v_outlier_idx;
+      p.Lmax = Lmax; p.L = L; p.score_stride = stride; p.H = H; p.n_out = n_out; p.fused = 1;
+      rc = v_accum_dispatch(bits, p, vcache, &n_cta, st);
+    }
     if (rc) return rc;
   }
   attend_combine_kernel<<<H, kHeadDim, 0, st>>>(part_o, part_l, n_cta, H, gmax, sink_scores,

@@ -134,6 +134,8 @@ def fill_layer_cache_gpu(lc, spec: SynthSpec, L: int, seed: int = 0, chunk: int 
         lc.kcache[:, :, sl] = qk.kcache[:, :, :T]
         lc.vcache[:, :, sl] = qv.vcache[:, :, :T]
         lc.vlut[sl] = qv.lookup_table[:T]
+        lc.vaff[sl, 0] = (uv[:, -1] - lv[:, -1]) / 2
+        lc.vaff[sl, 1] = (uv[:, -1] + lv[:, -1]) / 2
         lc.k_outliers[sl] = qk.outliers[:T]; lc.k_outlier_idx[sl] = qk.outlier_indices[:T]
         lc.v_outliers[sl] = qv.outliers[:T]; lc.v_outlier_idx[sl] = qv.outlier_indices[:T]
         done += T

@@ -208,6 +208,11 @@ def test_fused_device_append_matches_host_topk_path(bits):
     assert np.array_equal(lc.k_outliers.cpu().numpy(), c.k_out)
     assert np.array_equal(lc.v_outliers.cpu().numpy(), c.v_out)
     assert np.array_equal(lc.vlut.cpu().numpy(), c.vlut)
+    # per-token affine map consumed by the native V kernel: (sf, off) of modeling_llama.py:1097-1098
+    aff = lc.vaff.cpu().numpy()[:L]
+    for t in (0, 7, L - 1):
+        hi, lo, _, _ = O.v_thresholds(v[t], 21)
+        assert aff[t, 0] == np.float32((hi - lo) / np.float32(2)) and aff[t, 1] == np.float32((hi + lo) / np.float32(2))
 
 
 @pytest.mark.parametrize("bits,L,sparse,n_sink", [(4, 1100, True, 0), (3, 611, True, 5), (2, 530, True, 0),
@@ -245,6 +250,11 @@ def test_fused_attend_within_1e3_of_oracle_chain(bits, L, sparse, n_sink):
     out = lc.attend(cu(q), rope_theta=theta).cpu().numpy()
     e_max, e_l2 = rel_err(out, o_id)
     assert e_max < 1e-3 and e_l2 < 1e-3, (e_max, e_l2)
+    # the generic per-token-LUT V kernel (what a cache filled through the legacy ops uses) gives the same answer
+    lc.use_native_v = False
+    out_lut = lc.attend(cu(q), rope_theta=theta).cpu().numpy()
+    lc.use_native_v = True
+    assert rel_err(out_lut, o_id)[0] < 1e-3 and rel_err(out_lut, out)[0] < 1e-4
     if not n_sink:
         # and against the reference's own chain with its fp16 round trips (scores.half(), P.half(), out.half())
         p16, o16 = O.attend_reference(s, v_fn, 32)
