@@ -171,6 +171,17 @@ KVQ_API int kvq_append_v_orig(int32_t* cache, const float* lut_tok, const float*
                       float thr_lower, float thr_upper, int32_t* out_rows, float* out_vals,
                       int32_t* out_count, int H, int64_t Lmax, int64_t slot, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Decode-harness helpers (kvquant_b200/decode.py; NOT part of the reference's quant_cuda surface): fused fp16
+ * element-wise kernels around the hot path -- HF LlamaRMSNorm, rotate-half RoPE on Q + fp32 split of q/k/v
+ * (modeling_llama.py:1851-1859), SwiGLU activation, fp32->fp16 cast.  Pointers named *_f16 are __half*.
+ * ------------------------------------------------------------------------------------------------------------- */
+KVQ_API int kvq_dec_rmsnorm(const void* x_f16, const void* w_f16, void* y_f16, int n, float eps, void* stream);
+KVQ_API int kvq_dec_rope_split(const void* qkv_f16, const float* inv_freq, float pos, float* q, float* k, float* v,
+                               int hidden, void* stream);
+KVQ_API int kvq_dec_silu_mul(const void* gu_f16, void* act_f16, int n, void* stream);
+KVQ_API int kvq_dec_f32_to_f16(const float* a, void* b_f16, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

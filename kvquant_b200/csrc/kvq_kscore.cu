@@ -18,6 +18,7 @@
 //     channel are 16 distinct consecutive 8-byte slots -> conflict-free multicast for any code pattern.
 //   * per element: 1 code extract, 1 LDS.64, 2 FFMA.
 #include "kvq_common.cuh"
+#include <stdlib.h>
 
 namespace kvq {
 
@@ -260,6 +261,259 @@ __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// kappa form of the dense kernel (default).  The LDS.64 form above pays two shared-memory wavefronts per 32
+// elements; profiling (profiles/r01_*) showed the shared-memory pipe 68 % busy and `mio_throttle` the top stall.
+// Here the shared table holds the RAW per-channel LUT (4 bytes per entry -> one wavefront per 32 elements) and the
+// query-dependent factor is applied arithmetically per (head, pair, token):
+//
+//     kappa = cos*(q_c, q_c64) + sin*(q_c64, -q_c)            2 packed ops, q pairs are uniform operands from the
+//     acc  += (LUT_c[code_c], LUT_c64[code_c64]) * kappa      constant bank (LDCU.128 -> FMUL2 / FFMA2 UR operands)
+//
+// per pair: 2 PRMT + 2 LDS.32 + LDCU.128 + FMUL2 + 2 FFMA2  = 4 issue slots and 1 shared wavefront per element.
+// The rotated-query constants live in __constant__ memory, refreshed per call by a tiny prep kernel + a D2D
+// cudaMemcpyToSymbolAsync (stream-ordered, graph-capturable).  K launches of one device must be stream-ordered.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kMaxConstHeads = 48;
+__constant__ float4 c_qrot[kMaxConstHeads * kHalf];   // [h][j] = (q_c, q_c64, q_c64, -q_c), c = j < 64
+
+template <int BITS> struct KKCfg {
+  static constexpr int N = 1 << BITS;
+  static constexpr int W = Layout<BITS>::kWords;
+  static constexpr int CS = (N * 4 < 32) ? 32 : N * 4;   // bytes per channel in the table (8 channels = multiple of 256 B)
+  static constexpr int G = (BITS == 4) ? 16 : 32;        // heads per CTA: table = G*128*CS = 128 KiB
+  static constexpr int kThreads = 512;
+  static constexpr int TT = kThreads;
+  static constexpr int NRW = (BITS == 3) ? 4 : 2;
+  static constexpr int D = 4;                            // cp.async prefetch distance in work items
+};
+
+template <int IMM>
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+  float v;
+  asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
+  return v;
+}
+__device__ __forceinline__ float2 fmul2(const float2 a, const float2 b) {
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd; }"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+
+// one work item (head h (global), chunk a): 8 pairs
+template <int BITS>
+__device__ __forceinline__ void kk_item(const uint32_t* __restrict__ w, const int a, const uint32_t base, const int hq,
+                                        const float2* __restrict__ cs, float2& acc) {
+  using C = KKCfg<BITS>;
+  constexpr int CS = C::CS;
+  constexpr int HI = kHalf * CS;
+  uint32_t alo[8], ahi[8];
+  if constexpr (BITS == 4) {
+    const uint32_t e0 = (w[0] << 2) & 0x3C3C3C3Cu, o0 = (w[0] >> 2) & 0x3C3C3C3Cu;
+    const uint32_t e1 = (w[1] << 2) & 0x3C3C3C3Cu, o1 = (w[1] >> 2) & 0x3C3C3C3Cu;
+    static_for<0, 8>([&](auto ik) {
+      constexpr int k = decltype(ik)::v;
+      alo[k] = __byte_perm((k & 1) ? o0 : e0, base, 0x7650 | (k >> 1));
+      ahi[k] = __byte_perm((k & 1) ? o1 : e1, base, 0x7650 | (k >> 1));
+    });
+  } else if constexpr (BITS == 2) {
+    const int sh = 16 * (a & 1);
+    const uint32_t x0 = w[0] >> sh, x1 = w[1] >> sh;
+    const uint32_t m00 = (x0 << 2) & 0x0C0Cu, m01 = x0 & 0x0C0Cu, m02 = (x0 >> 2) & 0x0C0Cu, m03 = (x0 >> 4) & 0x0C0Cu;
+    const uint32_t m10 = (x1 << 2) & 0x0C0Cu, m11 = x1 & 0x0C0Cu, m12 = (x1 >> 2) & 0x0C0Cu, m13 = (x1 >> 4) & 0x0C0Cu;
+    static_for<0, 8>([&](auto ik) {
+      constexpr int k = decltype(ik)::v;
+      const uint32_t s0 = (k & 3) == 0 ? m00 : ((k & 3) == 1 ? m01 : ((k & 3) == 2 ? m02 : m03));
+      const uint32_t s1 = (k & 3) == 0 ? m10 : ((k & 3) == 1 ? m11 : ((k & 3) == 2 ? m12 : m13));
+      alo[k] = __byte_perm(s0, base, 0x7650 | (k >> 2));
+      ahi[k] = __byte_perm(s1, base, 0x7650 | (k >> 2));
+    });
+  } else {
+    const int sh = (24 * (a & 3)) & 31;
+    const uint32_t x0 = __funnelshift_r(w[0], w[1], sh), x1 = __funnelshift_r(w[2], w[3], sh);
+    static_for<0, 8>([&](auto ik) {
+      constexpr int k = decltype(ik)::v;
+      alo[k] = ((3 * k >= 2 ? (x0 >> (3 * k - 2)) : (x0 << (2 - 3 * k))) & 0x1Cu) | base;
+      ahi[k] = ((3 * k >= 2 ? (x1 >> (3 * k - 2)) : (x1 << (2 - 3 * k))) & 0x1Cu) | base;
+    });
+  }
+  static_for<0, 8>([&](auto ik) {
+    constexpr int k = decltype(ik)::v;
+    const float2 x = make_float2(lds_f1<k * CS>(alo[k]), lds_f1<k * CS + HI>(ahi[k]));
+    const float4 qr = c_qrot[hq * kHalf + 8 * a + k];   // uniform: one LDCU.128
+    const float2 kap = [&] {
+      const float2 t = fmul2(make_float2(cs[k].y, cs[k].y), make_float2(qr.z, qr.w));
+      float2 r = t;
+      ffma2(r, make_float2(cs[k].x, cs[k].x), make_float2(qr.x, qr.y));
+      return r;
+    }();
+    ffma2(acc, x, kap);
+  });
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(KKCfg<BITS>::kThreads, 1) k_scores_kappa_kernel(const KParams p) {
+  using C = KKCfg<BITS>;
+  constexpr int N = C::N, W = C::W, G = C::G, TT = C::TT, NRW = C::NRW, D = C::D, CS = C::CS;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((256u - (smem_u32(smem_raw) & 255u)) & 255u);
+  unsigned char* s_tab = smem;                                                   // [G][128][CS bytes]
+  uint32_t* s_ring = reinterpret_cast<uint32_t*>(smem + (size_t)G * kHeadDim * CS);  // [D][NRW][TT]
+
+  const int tid = threadIdx.x;
+  const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+  const int h0 = blockIdx.y * G;
+  const int nh = min(G, p.H - h0);
+
+  // raw per-channel LUT, CS bytes per channel
+  for (int i = tid; i < nh * kHeadDim * N; i += C::kThreads) {
+    const int hc = i / N, code = i - hc * N;
+    *reinterpret_cast<float*>(s_tab + (size_t)hc * CS + code * 4) = p.lut[((int64_t)h0 * kHeadDim) * N + i];
+  }
+  __syncthreads();
+  const uint32_t tab0 = smem_u32(s_tab);
+  const uint32_t ring0 = smem_u32(s_ring) + tid * 4;
+
+  const int64_t tile_first = (int64_t)blockIdx.x * p.tiles_per_cta;
+  const int64_t tile_end = min(tile_first + p.tiles_per_cta, (p.L + TT - 1) / TT);
+  const int64_t t_limit = min(p.L, tile_end * TT);
+  const uint32_t* cbase = p.cache + (int64_t)h0 * W * p.Lmax;
+  const uint32_t pitch = (uint32_t)p.Lmax * 4u;
+  const unsigned char* cb0 = reinterpret_cast<const unsigned char*>(cbase);
+  int64_t t_cur = tile_first * TT + tid;
+  auto prefetch = [&](int nxt, int a, int hl, int slot) {
+    const int64_t t = t_cur + (nxt ? TT : 0);
+    const int ok = (t < t_limit) && (hl < nh);
+    const unsigned char* src = cb0 + t * 4;
+#pragma unroll
+    for (int i = 0; i < NRW; ++i)
+      cp_async4(ring0 + (uint32_t)(slot * NRW + i) * (TT * 4),
+                src + (uint64_t)(uint32_t)(hl * W + chunk_word_row<BITS>(a, i)) * pitch, pol_stream, ok);
+    cp_async_commit();
+  };
+  auto load_cs = [&](float2* dst, int64_t tile, int a) {
+    const int64_t t = tile * TT + tid;
+    if (t < t_limit) {
+      const float2* rp = p.rope + (t + p.pos_offset) + (int64_t)(8 * a) * p.rope_npos;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dst[k] = ld_keep_f2(rp + (int64_t)k * p.rope_npos, pol_keep);
+    }
+  };
+
+  static_for<0, D>([&](auto id) {
+    constexpr int d = decltype(id)::v;
+    prefetch((d / G) / 8, (d / G) % 8, d % G, d % D);
+  });
+  float2 cs[8], csn[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { cs[k] = make_float2(0.f, 0.f); csn[k] = make_float2(0.f, 0.f); }
+  load_cs(cs, tile_first, 0);
+
+  for (int64_t tile = tile_first; tile < tile_end; ++tile) {
+    const int64_t t = tile * TT + tid;
+    t_cur = t;
+    const bool live = t < p.L;
+    float2 acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = make_float2(0.f, 0.f);
+
+    for (int a = 0; a < 8; ++a) {
+      load_cs(csn, a == 7 ? tile + 1 : tile, (a + 1) & 7);
+      static_for<0, G>([&](auto ig) {
+        constexpr int hl = decltype(ig)::v;
+        cp_async_wait<D - 1>();
+        uint32_t w[NRW];
+        constexpr int slot = hl % D;
+#pragma unroll
+        for (int i = 0; i < NRW; ++i) w[i] = lds_u32(ring0 + (uint32_t)(slot * NRW + i) * (TT * 4));
+        {
+          constexpr int hn = (hl + D) % G;
+          constexpr int wrap = (hl + D) / G;
+          const int an = a + wrap;
+          prefetch(an >> 3, an & 7, hn, slot);
+        }
+        // no per-thread guard here: lanes past L compute on stale ring words (always in-bounds table reads) and are
+        // masked at the store; keeping the region convergent lets the q constants use the uniform datapath (LDCU)
+        if (hl < nh)
+          kk_item<BITS>(w, a, tab0 + (uint32_t)hl * (kHeadDim * CS) + (uint32_t)a * (8 * CS), h0 + hl, cs, acc[hl]);
+      });
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cs[k] = csn[k];
+    }
+
+#pragma unroll
+    for (int hl = 0; hl < G; ++hl) {
+      if (hl < nh) {
+        float s = acc[hl].x + acc[hl].y;
+        if (live) {
+          float* o = p.out + (int64_t)(h0 + hl) * p.out_stride + t;
+          if (p.accumulate) s += *o;
+          s *= p.scale;
+          *o = s;
+        }
+        if (p.gmax != nullptr) {
+          const float m = warp_max(live ? s : -INFINITY);
+          if ((tid & 31) == 0 && m > -INFINITY) atomic_max_float(p.gmax + h0 + hl, m);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+// rotated-query constants: scratch[h*64+j] = (q_c, q_c64, q_c64, -q_c)
+__global__ void k_qrot_prep_kernel(const float* __restrict__ q, float4* __restrict__ scratch, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * kHalf) return;
+  const int h = i / kHalf, j = i - h * kHalf;
+  const float a = q[h * kHeadDim + j], b = q[h * kHeadDim + j + kHalf];
+  scratch[i] = make_float4(a, b, b, -a);
+}
+
+static float4* g_qrot_scratch[32] = {nullptr};
+
+static int upload_qrot(const float* q, int H, cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 32) return KVQ_E_UNSUPPORTED;
+  if (!g_qrot_scratch[dev]) {
+    cudaError_t e = cudaMalloc(&g_qrot_scratch[dev], sizeof(float4) * kMaxConstHeads * kHalf);
+    if (e != cudaSuccess) return (int)e;
+  }
+  k_qrot_prep_kernel<<<(H * kHalf + 255) / 256, 256, 0, st>>>(q, g_qrot_scratch[dev], H);
+  KVQ_LAUNCH_CHECK();
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_qrot, g_qrot_scratch[dev], sizeof(float4) * H * kHalf, 0,
+                                          cudaMemcpyDeviceToDevice, st);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+template <int BITS>
+static int launch_k_kappa(const KParams& p, cudaStream_t st) {
+  using C = KKCfg<BITS>;
+  const size_t smem = 256 + (size_t)C::G * kHeadDim * C::CS + (size_t)C::D * C::NRW * C::TT * 4;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k_scores_kappa_kernel<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  int rc = upload_qrot(p.q, p.H, st);
+  if (rc != 0) return rc;
+  const int n_groups = (p.H + C::G - 1) / C::G;
+  const int64_t n_tiles = (p.L + C::TT - 1) / C::TT;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t max_splits = sms / n_groups > 0 ? sms / n_groups : 1;
+  KParams q = p;
+  q.tiles_per_cta = (int)((n_tiles + max_splits - 1) / max_splits);
+  const int64_t splits = (n_tiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
+  k_scores_kappa_kernel<BITS><<<dim3((unsigned)splits, (unsigned)n_groups), C::kThreads, smem, st>>>(q);
+  KVQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Outlier pre-pass (replaces SPMV_ATOMIC_ROPE_BALANCED, quant_cuda_kernel.cu:472-521): thread = token, walks the
 // token's n_out (value, channel) pairs, RoPE evaluated with the reference's own expressions (theta from a 64-entry
 // powf table, cosf/sinf of theta*pos) -- 42 sincos per token instead of the dense path's former 4096.  The row is
@@ -383,7 +637,21 @@ static int launch_k_scores(const KParams& p, cudaStream_t st) {
   return 0;
 }
 
+static int k_impl_lds64() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("KVQ_K_IMPL"); v = (e && e[0] == 'l') ? 1 : 0; }  // KVQ_K_IMPL=lds64 -> A/B switch
+  return v;
+}
+
 int k_scores_dispatch(int bits, const KParams& p, cudaStream_t st) {
+  if (p.H <= kMaxConstHeads && !k_impl_lds64()) {
+    switch (bits) {
+      case 4: return launch_k_kappa<4>(p, st);
+      case 3: return launch_k_kappa<3>(p, st);
+      case 2: return launch_k_kappa<2>(p, st);
+      default: return KVQ_E_BITS;
+    }
+  }
   switch (bits) {
     case 4: return launch_k_scores<4>(p, st);
     case 3: return launch_k_scores<3>(p, st);

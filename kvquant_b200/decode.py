@@ -119,18 +119,56 @@ class DecoderStage:
         rot = torch.cat((-q[:, self._half:], q[:, :self._half]), dim=-1)
         return q * cos + rot * sin
 
+    def _buffers(self):
+        if getattr(self, "_buf", None) is None:
+            cfg, dev = self.cfg, self.device
+            f16 = dict(dtype=torch.float16, device=dev)
+            f32 = dict(dtype=torch.float32, device=dev)
+            self._buf = dict(h=torch.empty(cfg.hidden, **f16), qkv=torch.empty(3 * cfg.hidden, **f16),
+                             q=torch.empty(cfg.hidden, **f32), k=torch.empty(cfg.hidden, **f32),
+                             v=torch.empty(cfg.hidden, **f32), o16=torch.empty(cfg.hidden, **f16),
+                             gu=torch.empty(2 * cfg.intermediate, **f16), act=torch.empty(cfg.intermediate, **f16))
+        return self._buf
+
     def forward(self, x):
-        """x: fp16 [hidden] -> fp16 [hidden] after this stage's layers; appends one token to every layer cache."""
+        """x: fp16 [hidden] -> fp16 [hidden] after this stage's layers; appends one token to every layer cache.
+        GEMVs are cuBLAS (torch.mv / addmv); RMSNorm, RoPE+split, SwiGLU and the cast are fused helper kernels of the
+        library (kvq_dec_*), everything touching the KV cache is kvq_append_kv_fused + kvq_attend."""
+        from . import _lib
+        cfg = self.cfg
+        lib = _lib.load()
+        b = self._buffers()
+        H, hid, it = cfg.n_heads, cfg.hidden, cfg.intermediate
+        st = torch.cuda.current_stream().cuda_stream
+        for ly in self.layers:
+            c = ly.cache
+            pos = c.n_sink + c.len                       # absolute position of the new token
+            _lib.check(lib.kvq_dec_rmsnorm(x.data_ptr(), ly.n1.data_ptr(), b["h"].data_ptr(), hid, cfg.rms_eps, st))
+            torch.mv(ly.wqkv, b["h"], out=b["qkv"])
+            _lib.check(lib.kvq_dec_rope_split(b["qkv"].data_ptr(), self.inv_freq.data_ptr(), float(pos),
+                                              b["q"].data_ptr(), b["k"].data_ptr(), b["v"].data_ptr(), hid, st))
+            c.append(b["k"], b["v"])                     # pre-RoPE K, per-token V: quantise + outlier split
+            o = c.attend(b["q"].view(H, HEAD_DIM), rope_theta=cfg.rope_theta)   # f32 [H,128]
+            _lib.check(lib.kvq_dec_f32_to_f16(o.data_ptr(), b["o16"].data_ptr(), hid, st))
+            x = torch.addmv(x, ly.wo, b["o16"])
+            _lib.check(lib.kvq_dec_rmsnorm(x.data_ptr(), ly.n2.data_ptr(), b["h"].data_ptr(), hid, cfg.rms_eps, st))
+            torch.mv(ly.wgu, b["h"], out=b["gu"])
+            _lib.check(lib.kvq_dec_silu_mul(b["gu"].data_ptr(), b["act"].data_ptr(), it, st))
+            x = torch.addmv(x, ly.wdown, b["act"])
+        return x
+
+    def forward_torch(self, x):
+        """Same dataflow with plain torch element-wise ops (reference for the helper kernels; used by tests)."""
         cfg = self.cfg
         H = cfg.n_heads
         for ly in self.layers:
             c = ly.cache
-            pos = c.n_sink + c.len                       # absolute position of the new token
+            pos = c.n_sink + c.len
             qkv = ly.wqkv @ rmsnorm(x, ly.n1, cfg.rms_eps)
             q, k, v = qkv.float().split(cfg.hidden)
             q = self._rope_q(q.view(H, HEAD_DIM), pos).contiguous()
-            c.append(k.contiguous(), v.contiguous())     # pre-RoPE K, per-token V: quantise + outlier split
-            o = c.attend(q, rope_theta=cfg.rope_theta)   # f32 [H,128]
+            c.append(k.contiguous(), v.contiguous())
+            o = c.attend(q, rope_theta=cfg.rope_theta)
             x = x + ly.wo @ o.half().view(-1)
             gu = ly.wgu @ rmsnorm(x, ly.n2, cfg.rms_eps)
             g, u = gu.split(cfg.intermediate)

@@ -44,6 +44,8 @@ def main():
     log = open(os.path.join(OUT, "probe.jsonl"), "a")
 
     def emit(**kw):
+        if os.environ.get("PROBE_TAG"):
+            kw["tag"] = os.environ["PROBE_TAG"]
         print(json.dumps(kw), flush=True)
         log.write(json.dumps(kw) + "\n"); log.flush()
 
@@ -92,7 +94,7 @@ def main():
                 torch.cuda.synchronize()
                 continue
             # ---- correctness at full size against the reference kernels --------------------------------------
-            if ref is not None and L <= 1 << 20:
+            if ref is not None and L <= 1 << 20 and not os.environ.get("PROBE_SKIP_REF"):
                 for nm, runner, buf in (("k_opt2", run_k, mulK), ("v_opt2", run_v, mulV), ("k_opt", run_kd, mulK), ("v_opt", run_vd, mulV)):
                     buf.zero_(); runner(qc); ours = buf.clone()
                     buf.zero_(); runner(ref); theirs = buf.clone()
@@ -104,7 +106,7 @@ def main():
                                        ("k_opt", run_kd, L * H * 128 * bits // 8), ("v_opt", run_vd, L * (H * 128 * bits // 8 + 4 * 2 ** bits))):
                 med, best = timeit(lambda: runner(qc))
                 emit(event="time", impl="ours", op=nm, bits=bits, L=L, ms=med, best_ms=best, gbs=nbytes / med / 1e6, frac=nbytes / med / 1e6 / PEAK)
-                if ref is not None and L <= 1 << 18:
+                if ref is not None and L <= 1 << 18 and not os.environ.get("PROBE_SKIP_REF"):
                     med, best = timeit(lambda: runner(ref), iters=5, warm=1)
                     emit(event="time", impl="reference_cuda", op=nm, bits=bits, L=L, ms=med, best_ms=best, gbs=nbytes / med / 1e6, frac=nbytes / med / 1e6 / PEAK)
             qa = q[0].contiguous()

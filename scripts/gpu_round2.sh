@@ -7,12 +7,14 @@ tail -15 gpurun_out/pytest_gpu.log
 rm -f gpurun_out/probe.jsonl
 PROBE_BITS=${PROBE_BITS:-4,3} PROBE_L=${PROBE_L:-131072} timeout 600 python scripts/gpu_probe.py > gpurun_out/probe.log 2>&1; echo "probe rc=$?" >> gpurun_out/probe.log
 grep -E '"impl": "ours"|rc=|Error|error' gpurun_out/probe.log | tail -20
+KVQ_K_IMPL=lds64 PROBE_TAG=lds64 PROBE_SKIP_REF=1 PROBE_BITS=${PROBE_BITS:-4,3} PROBE_L=${PROBE_L:-131072} timeout 600 python scripts/gpu_probe.py > gpurun_out/probe_lds64.log 2>&1
+grep -E '"op": "k_opt' gpurun_out/probe_lds64.log | tail -8
 if [ "${RUN_BENCH:-1}" = "1" ]; then
   timeout 900 python bench.py --steps 10 --warmup 3 ${BENCH_ARGS} > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
   tail -3 gpurun_out/bench.log; tail -5 gpurun_out/bench.err
 fi
 if [ "${RUN_NCU:-1}" = "1" ]; then
-  PROBE_QUICK=1 PROBE_BITS=4,3 PROBE_L=131072 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_probe.csv python scripts/gpu_probe.py > gpurun_out/ncu_list.log 2>&1
-  PROBE_QUICK=1 PROBE_BITS=4 PROBE_L=131072 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_scores_kernel|v_accum_kernel|k_outlier_kernel' -s 3 -c 8 -o gpurun_out/prof_kv python scripts/gpu_probe.py > gpurun_out/ncu_full.log 2>&1
+  PROBE_QUICK=1 PROBE_BITS=4,3 PROBE_L=131072 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_scores|v_accum|v_native|k_outlier|attend_|k_qrot' -c 400 --csv --log-file gpurun_out/launches_probe.csv python scripts/gpu_probe.py > gpurun_out/ncu_list.log 2>&1
+  PROBE_QUICK=1 PROBE_BITS=4 PROBE_L=131072 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_scores|v_native|k_outlier' -s 4 -c 8 -o gpurun_out/prof_kv python scripts/gpu_probe.py > gpurun_out/ncu_full.log 2>&1
   ls -la gpurun_out | tail -12
 fi
