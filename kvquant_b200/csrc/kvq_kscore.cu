@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// kappa form of the dense kernel (default).  The LDS.64 form above pays two shared-memory wavefronts per 32
+// kappa form of the dense kernel (alternative, KVQ_K_IMPL=kappa).  The LDS.64 form above pays two shared-memory wavefronts per 32
 // elements; profiling (profiles/r01_*) showed the shared-memory pipe 68 % busy and `mio_throttle` the top stall.
 // Here the shared table holds the RAW per-channel LUT (4 bytes per entry -> one wavefront per 32 elements) and the
 // query-dependent factor is applied arithmetically per (head, pair, token):
@@ -523,7 +523,7 @@ static int launch_k_kappa(const KParams& p, cudaStream_t st) {
 // store_all = 0: only heads with outliers are touched, out += contribution (legacy accumulate semantics).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kOutThreads = 256;
-constexpr int kOutBatch = 6;   // (value, index) pairs fetched per thread before they are consumed
+constexpr int kOutBatch = 14;   // (value, index) pairs fetched per thread before they are consumed
 
 __global__ void __launch_bounds__(kOutThreads) k_outlier_kernel(
     const float* __restrict__ q, const float* __restrict__ outliers, const int32_t* __restrict__ outlier_idx,
@@ -638,8 +638,10 @@ static int launch_k_scores(const KParams& p, cudaStream_t st) {
 }
 
 static int k_impl_lds64() {
+  // default: the LDS.64 form (measured faster on B200: 197 us vs 253 us for 4-bit / 128K, profiles/r01_*);
+  // KVQ_K_IMPL=kappa selects the 4-byte-entry kappa form for A/B runs
   static int v = -1;
-  if (v < 0) { const char* e = getenv("KVQ_K_IMPL"); v = (e && e[0] == 'l') ? 1 : 0; }  // KVQ_K_IMPL=lds64 -> A/B switch
+  if (v < 0) { const char* e = getenv("KVQ_K_IMPL"); v = (e && e[0] == 'k') ? 0 : 1; }
   return v;
 }
 

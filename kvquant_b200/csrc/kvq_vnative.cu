@@ -20,9 +20,9 @@
 namespace kvq {
 
 constexpr int kNThreads = 512;
-constexpr int kNT = 16;          // tokens per stage
-constexpr int kNMaxStages = 4;
-constexpr int kNMaxOPre = 2;     // prefetched outlier entries per thread (16*n_out/512 <= 2 -> n_out <= 64)
+constexpr int kNT = 32;          // tokens per stage (128-byte rows, 128B swizzle)
+constexpr int kNMaxStages = 3;
+constexpr int kNTokPerWarp = kNT / (kNThreads / 32);   // outlier rows handled by one warp per tile (2)
 
 struct VNParams {
   const float* score;        // [H, score_stride] scaled scores
@@ -34,7 +34,7 @@ struct VNParams {
   const float* outliers;     // [>=L, n_out] or null
   const int32_t* outlier_idx;
   int64_t Lmax, L, score_stride;
-  int H, n_out, tiles_per_cta, n_stages;
+  int H, n_out, tiles_per_cta, n_stages, box_rows;
 };
 
 template <int BITS> struct VNCfg {
@@ -69,14 +69,14 @@ __device__ __forceinline__ void ffma2v(float2& acc, const float2 a, const float2
       : "+f"(acc.x), "+f"(acc.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
 }
 
-// 16 tokens of one unit.  row_off/swz: this unit's word row in the 64B-swizzled stage; tab = shared address of the
-// lane's table column (table base + lane*8); wsrow -> ws[head][0..15].
+// 32 tokens of one unit.  row_off/swz: this unit's word row in the 128B-swizzled stage; tab = shared address of the
+// lane's table column (table base + lane*8); wsrow -> ws[head][0..31].
 template <int BITS, int SUB>
 __device__ __forceinline__ void vn_tile_unit(const unsigned char* stage, uint32_t row_off, uint32_t swz,
                                              uint32_t row_off2, uint32_t swz2, int part, uint32_t tab,
                                              const float* __restrict__ wsrow, float2* __restrict__ acc) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
+#pragma unroll 2
+  for (int q = 0; q < 8; ++q) {
     const uint4 wa = *reinterpret_cast<const uint4*>(stage + row_off + ((q ^ swz) << 4));
     uint4 wb = make_uint4(0, 0, 0, 0);
     if constexpr (BITS == 3 && SUB < 2) wb = *reinterpret_cast<const uint4*>(stage + row_off2 + ((q ^ swz2) << 4));
@@ -166,16 +166,17 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
       else { u_row[i] = u >> 1; u_part[i] = u & 1; u_head[i] = u >> 4; u_ch0[i] = ((u >> 1) & 7) * 16 + (u & 1) * 8; }
     }
   }
-  // 64B swizzle: 16-byte chunk index ^= (row >> 1) & 3 ; boxes of 32 rows x 64 B = 2048 B
+  // 128B swizzle: 16-byte chunk index ^= row & 7; TMA boxes are [32 tokens x box_rows rows] (box_rows % 8 == 0), laid
+  // out back to back, so row r simply sits at r*128 inside the stage
   uint32_t r_off[2], r_swz[2], r_off2[2], r_swz2[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int r = u_on[i] ? u_row[i] : 0;
-    r_off[i] = (uint32_t)(r >> 5) * 2048u + (uint32_t)(r & 31) * 64u;
-    r_swz[i] = (uint32_t)((r >> 1) & 3);
+    r_off[i] = (uint32_t)r * 128u;
+    r_swz[i] = (uint32_t)(r & 7);
     const int r2 = (r + 1 < rows) ? r + 1 : r;
-    r_off2[i] = (uint32_t)(r2 >> 5) * 2048u + (uint32_t)(r2 & 31) * 64u;
-    r_swz2[i] = (uint32_t)((r2 >> 1) & 3);
+    r_off2[i] = (uint32_t)r2 * 128u;
+    r_swz2[i] = (uint32_t)(r2 & 7);
   }
   float2 acc[2][NP];
 #pragma unroll
@@ -193,59 +194,75 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
   const int64_t n_tiles_total = (p.L + kNT - 1) / kNT;
   const int64_t tile0 = (int64_t)blockIdx.x * p.tiles_per_cta;
   const int ntiles = (int)max((int64_t)0, min((int64_t)p.tiles_per_cta, n_tiles_total - tile0));
-  const int nbox = rows >> 5;
+  const int nbox = rows / p.box_rows;
 
   auto issue_tile = [&](int it) {  // thread 0 only
     const int s = it % S;
     const int64_t t0 = (tile0 + it) * kNT;
     mbar_expect_tx(&s_bar[s], lay.stage_bytes);
     unsigned char* dst = smem + (size_t)s * lay.stage_bytes;
-    for (int b = 0; b < nbox; ++b) tma_load_2d(dst + b * 2048, &tmap, &s_bar[s], (int)t0, b * 32);
+    for (int b = 0; b < nbox; ++b) tma_load_2d(dst + (size_t)b * p.box_rows * 128, &tmap, &s_bar[s], (int)t0, b * p.box_rows);
   };
-  // weights: one (head, token) value per thread per tile (H*16 <= 1024 -> up to 2)
+  // weights: H*32 (head, token) values per tile -> 2 per thread at H = 32 (up to 4 at H = 64)
   const int n_w = p.H * kNT;
-  float wpre[2], wspre[2];
-  float lacc[2] = {0.f, 0.f}, oacc_off[2] = {0.f, 0.f};
+  constexpr int NW = 4;
+  float wpre[NW], wspre[NW], offpre[NW];
+  float lacc[NW], oacc_off[NW];
+#pragma unroll
+  for (int i = 0; i < NW; ++i) { lacc[i] = 0.f; oacc_off[i] = 0.f; wpre[i] = wspre[i] = offpre[i] = 0.f; }
+  // raw loads only (consumed in finish_weights after the tile's compute, so their latency is hidden)
+  float w_s[NW], w_m[NW];
+  float2 w_a[NW];
   auto load_weights = [&](int it) {
     const int64_t t0 = (tile0 + it) * kNT;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NW; ++i) {
       const int e = tid + i * kNThreads;
-      float w = 0.f, ws = 0.f;
+      w_s[i] = -INFINITY; w_m[i] = 0.f; w_a[i] = make_float2(0.f, 0.f);
       if (e < n_w) {
-        const int h = e >> 4, tl = e & 15;
+        const int h = e >> 5, tl = e & 31;
         if (t0 + tl < p.L) {
-          w = __expf(p.score[(int64_t)h * p.score_stride + t0 + tl] - p.gmax[h]);
-          const float2 a = *reinterpret_cast<const float2*>(p.v_aff + 2 * (t0 + tl));
-          ws = w * a.x;
-          lacc[i] += w;
-          oacc_off[i] = fmaf(w, a.y, oacc_off[i]);
+          w_s[i] = p.score[(int64_t)h * p.score_stride + t0 + tl];
+          w_m[i] = p.gmax[h];
+          w_a[i] = *reinterpret_cast<const float2*>(p.v_aff + 2 * (t0 + tl));
         }
       }
-      wpre[i] = w; wspre[i] = ws;
+    }
+  };
+  auto finish_weights = [&]() {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      const float w = (w_s[i] == -INFINITY) ? 0.f : __expf(w_s[i] - w_m[i]);
+      wpre[i] = w;
+      wspre[i] = w * w_a[i].x;
+      lacc[i] += w;
+      oacc_off[i] = fmaf(w, w_a[i].y, oacc_off[i]);
     }
   };
   auto store_weights = [&](int buf) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NW; ++i) {
       const int e = tid + i * kNThreads;
       if (e < n_w) { s_w[buf * n_w + e] = wpre[i]; s_ws[buf * n_w + e] = wspre[i]; }
     }
   };
-  float opre_v[kNMaxOPre];
-  int opre_i[kNMaxOPre];
+  // outliers: warp w owns tokens {w, w+16} of the tile; lanes walk the row (no divisions), prefetched into registers
+  constexpr int NO = 2 * kNTokPerWarp;   // (value, index) pairs per lane per tile for n_out <= 64
+  float opre_v[NO];
+  int opre_i[NO];
   const bool has_out = p.outliers != nullptr;
   auto load_outliers = [&](int it) {
     const int64_t t0 = (tile0 + it) * kNT;
-    const int ntok = (int)min((int64_t)kNT, p.L - t0);
-    const int total = ntok * p.n_out;
-    const float* ov = p.outliers + t0 * p.n_out;
-    const int32_t* oi = p.outlier_idx + t0 * p.n_out;
 #pragma unroll
-    for (int i = 0; i < kNMaxOPre; ++i) {
-      const int e = tid + i * kNThreads;
-      opre_v[i] = 0.f; opre_i[i] = 0;
-      if (e < total) { opre_v[i] = ov[e]; opre_i[i] = oi[e]; }
+    for (int j = 0; j < kNTokPerWarp; ++j) {
+      const int64_t t = t0 + warp + j * (kNThreads / 32);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int k = lane + 32 * r;
+        const bool in = (t < p.L) && (k < p.n_out);
+        opre_v[2 * j + r] = in ? p.outliers[t * p.n_out + k] : 0.f;
+        opre_i[2 * j + r] = in ? p.outlier_idx[t * p.n_out + k] : 0;
+      }
     }
   };
 
@@ -254,6 +271,7 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
     if (tid == 0)
       for (int it = 0; it < S - 1 && it < ntiles; ++it) issue_tile(it);
     load_weights(0);
+    finish_weights();
     store_weights(0);
   }
 
@@ -282,24 +300,28 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
     }
     if (has_out) {
       const float* wbuf = s_w + (it & 1) * n_w;
-      const int64_t t0 = (tile0 + it) * kNT;
-      const int ntok = (int)min((int64_t)kNT, p.L - t0);
-      const int total = ntok * p.n_out;
 #pragma unroll
-      for (int i = 0; i < kNMaxOPre; ++i) {
-        const int e = tid + i * kNThreads;
-        if (e < total && opre_v[i] != 0.f) {
-          const int idx = opre_i[i];
-          atomicAdd(&s_oacc[idx], opre_v[i] * wbuf[(idx >> 7) * kNT + e / p.n_out]);
+      for (int j = 0; j < kNTokPerWarp; ++j) {
+        const int tl = warp + j * (kNThreads / 32);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const float v = opre_v[2 * j + r];
+          if (v != 0.f) {
+            const int idx = opre_i[2 * j + r];
+            atomicAdd(&s_oacc[idx], v * wbuf[(idx >> 7) * kNT + tl]);
+          }
+        }
+        for (int k = lane + 64; k < p.n_out; k += 32) {   // n_out > 64: unprefetched tail
+          const int64_t t = (tile0 + it) * kNT + tl;
+          if (t < p.L) {
+            const float v = p.outliers[t * p.n_out + k];
+            const int idx = p.outlier_idx[t * p.n_out + k];
+            if (v != 0.f) atomicAdd(&s_oacc[idx], v * wbuf[(idx >> 7) * kNT + tl]);
+          }
         }
       }
-      for (int e = tid + kNMaxOPre * kNThreads; e < total; e += kNThreads) {
-        const float v = p.outliers[t0 * p.n_out + e];
-        const int idx = p.outlier_idx[t0 * p.n_out + e];
-        if (v != 0.f) atomicAdd(&s_oacc[idx], v * wbuf[(idx >> 7) * kNT + e / p.n_out]);
-      }
     }
-    if (more) store_weights((it + 1) & 1);
+    if (more) { finish_weights(); store_weights((it + 1) & 1); }
   }
   __syncthreads();
 
@@ -309,13 +331,11 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
   for (int i = tid; i < 2 * p.H; i += kNThreads) s_w[i] = 0.f;
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < NW; ++i) {
     const int e = tid + i * kNThreads;
-    // a half-warp's 16 slots are the 16 tokens of one head
-    float a = lacc[i], b = oacc_off[i];
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-    if (e < n_w && (lane & 15) == 0) { atomicAdd(&s_l[e >> 4], a); atomicAdd(&s_off[e >> 4], b); }
+    // a warp's 32 slots are the 32 tokens of one head
+    const float a = warp_sum(lacc[i]), b = warp_sum(oacc_off[i]);
+    if (e < n_w && lane == 0) { atomicAdd(&s_l[e >> 5], a); atomicAdd(&s_off[e >> 5], b); }
   }
   __syncthreads();
   for (int i = tid; i < p.H; i += kNThreads) p.out_l[(int64_t)blockIdx.x * p.H + i] = s_l[i];
@@ -359,7 +379,11 @@ static int launch_vn(VNParams p, const int32_t* cache, int* n_cta_out, cudaStrea
     attr_done = true;
   }
   CUtensorMap tmap;
-  int rc = make_cache_tensor_map(&tmap, cache, (uint64_t)rows, (uint64_t)p.Lmax, kNT, 32, /*swizzle bytes*/ 64);
+  // largest TMA box height <= 256 that divides the row count (rows is a multiple of 32)
+  int nb = (rows + 255) / 256;
+  while (rows % nb != 0 || (rows / nb) % 8 != 0) ++nb;
+  p.box_rows = rows / nb;
+  int rc = make_cache_tensor_map(&tmap, cache, (uint64_t)rows, (uint64_t)p.Lmax, kNT, (uint32_t)p.box_rows, /*swizzle bytes*/ 128);
   if (rc != 0) return rc;
   const int64_t n_tiles = (p.L + kNT - 1) / kNT;
   const int sms = num_sms_cached();
