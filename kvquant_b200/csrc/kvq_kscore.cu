@@ -25,7 +25,7 @@ namespace kvq {
 template <int BITS> struct KCfg {
   static constexpr int N = 1 << BITS;
   static constexpr int W = Layout<BITS>::kWords;
-  static constexpr int G = 128 / N;            // heads per CTA: 8 / 16 / 32 -> table = G*128*N*8 B = 128 KiB
+  static constexpr int G = (BITS == 2) ? 16 : 128 / N;  // heads per CTA: 8 / 16 / 16 -> table = 128 / 128 / 64 KiB
   static constexpr int kThreads = 512;
   static constexpr int TT = kThreads;          // tokens per tile (thread = token)
   static constexpr int NRW = (BITS == 3) ? 4 : 2;  // packed words a thread needs per (head, 8-pair chunk)
@@ -134,62 +134,68 @@ __device__ __forceinline__ void k_item(const uint32_t* __restrict__ w, const int
   }
 }
 
-template <int BITS>
+// FULL = the CTA owns a complete group of G heads (the common case: H % G == 0) -> no per-item head checks.
+template <int BITS, bool FULL>
 __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const KParams p) {
   using C = KCfg<BITS>;
-  constexpr int N = C::N, W = C::W, G = C::G, TT = C::TT, NRW = C::NRW, D = C::D;
+  constexpr int N = C::N, W = C::W, G = C::G, TT = C::TT, NRW = C::NRW;
+  constexpr int PD = 4;   // register prefetch distance in work items (G % PD == 0)
   extern __shared__ unsigned char smem_raw[];
   // table base must be 256-byte aligned (the low address byte carries code*8)
   unsigned char* smem = smem_raw + ((256u - (smem_u32(smem_raw) & 255u)) & 255u);
   float2* s_tab = reinterpret_cast<float2*>(smem);                  // [G][128][N]
   float* s_q = reinterpret_cast<float*>(s_tab + G * kHeadDim * N);   // [G][128]
-  uint32_t* s_ring = reinterpret_cast<uint32_t*>(s_q + G * kHeadDim);  // [D][NRW][TT]
 
   const int tid = threadIdx.x;
   const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
   const int h0 = blockIdx.y * G;
-  const int nh = min(G, p.H - h0);
+  const int nh = FULL ? G : min(G, p.H - h0);
 
   // ---- premultiplied tables T[hl][c][code] = (LUT*q[c], s_c*LUT*q[c^64]) -----------------------------------------
   for (int i = tid; i < nh * kHeadDim; i += C::kThreads) s_q[i] = p.q[(int64_t)h0 * kHeadDim + i];
   __syncthreads();
-  for (int i = tid; i < nh * kHeadDim * N; i += C::kThreads) {
-    const int hc = i / N;             // hl*128 + c
-    const int c = hc & (kHeadDim - 1);
-    const float l = p.lut[((int64_t)h0 * kHeadDim) * N + i];
-    const float qa = s_q[hc];
-    const float qb = s_q[hc ^ kHalf];  // (c+64)%128 within the same head
-    s_tab[i] = make_float2(l * qa, (c < kHalf) ? (l * qb) : -(l * qb));
+  for (int i = tid; i < G * kHeadDim * N; i += C::kThreads) {
+    float2 e = make_float2(0.f, 0.f);   // heads past nh: zero tables (their items still run, results are dropped)
+    if (i < nh * kHeadDim * N) {
+      const int hc = i / N;             // hl*128 + c
+      const int c = hc & (kHeadDim - 1);
+      const float l = p.lut[((int64_t)h0 * kHeadDim) * N + i];
+      const float qa = s_q[hc];
+      const float qb = s_q[hc ^ kHalf];  // (c+64)%128 within the same head
+      e = make_float2(l * qa, (c < kHalf) ? (l * qb) : -(l * qb));
+    }
+    s_tab[i] = e;
   }
   __syncthreads();
   const uint32_t tab0 = smem_u32(s_tab);
-  const uint32_t ring0 = smem_u32(s_ring) + tid * 4;
 
   // The CTA walks `tiles_per_cta` tiles of TT tokens; a thread's work items are linearised as
-  // (tile, chunk a = 0..7, head hl = 0..G-1) and the packed words of item i+D are fetched while item i computes.
+  // (tile, chunk a = 0..7, head hl = 0..G-1); the packed words of item i+PD are loaded into a rotating register
+  // buffer while item i computes, the rope values of the next chunk likewise.
   const int64_t tile_first = (int64_t)blockIdx.x * p.tiles_per_cta;
   const int64_t tile_end = min(tile_first + p.tiles_per_cta, (p.L + TT - 1) / TT);
   const int64_t t_limit = min(p.L, tile_end * TT);   // tokens this CTA may touch
-  const uint32_t* cbase = p.cache + (int64_t)h0 * W * p.Lmax;
+  const uint32_t pitch = (uint32_t)p.Lmax * 4u;      // row pitch in bytes (host checks Lmax < 2^30)
+  const unsigned char* cb0 = reinterpret_cast<const unsigned char*>(p.cache + (int64_t)h0 * W * p.Lmax);
 
-  // issue the copies of item (a, hl) of the current (nxt = 0) or next (nxt = 1) tile into ring slot `slot`, then commit
-  // (always exactly one group per item, so wait_group<D-1> means "the oldest outstanding item has landed").
-  // Row pitch in bytes fits 32 bits (host checks Lmax < 2^30); byte offsets are formed with one IMAD.WIDE per copy.
-  const uint32_t pitch = (uint32_t)p.Lmax * 4u;
-  const unsigned char* cb0 = reinterpret_cast<const unsigned char*>(cbase);
-  int64_t t_cur = tile_first * TT + tid;
-  auto prefetch = [&](int nxt, int a, int hl, int slot) {
-    const int64_t t = t_cur + (nxt ? TT : 0);
-    const int ok = (t < t_limit) && (hl < nh);
-    const unsigned char* src = cb0 + t * 4;
+  // pointers of the current / next tile's column for this thread, and whether those columns exist
+  const unsigned char* src_cur = cb0 + (tile_first * TT + tid) * 4;
+  bool ok_cur = (tile_first * TT + tid) < t_limit;
+
+  uint32_t wq[PD][NRW];   // rotating prefetch buffer (compile-time indices only)
 #pragma unroll
-    for (int i = 0; i < NRW; ++i)
-      cp_async4(ring0 + (uint32_t)(slot * NRW + i) * (TT * 4),
-                src + (uint64_t)(uint32_t)(hl * W + chunk_word_row<BITS>(a, i)) * pitch, pol_stream, ok);
-    cp_async_commit();
+  for (int d = 0; d < PD; ++d)
+#pragma unroll
+    for (int i = 0; i < NRW; ++i) wq[d][i] = 0;
+  auto fetch = [&](uint32_t* dst, const unsigned char* base, bool ok, int a, int hl) {
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < NRW; ++i)
+        dst[i] = ld_stream_u32(reinterpret_cast<const uint32_t*>(
+                                   base + (uint64_t)(uint32_t)(hl * W + chunk_word_row<BITS>(a, i)) * pitch), pol_stream);
+    }
   };
-  auto load_cs = [&](float2* dst, int64_t tile, int a) {
-    const int64_t t = tile * TT + tid;
+  auto load_cs = [&](float2* dst, const int64_t t, int a) {
     if (t < t_limit) {
       const float2* rp = p.rope + (t + p.pos_offset) + (int64_t)(8 * a) * p.rope_npos;
 #pragma unroll
@@ -197,67 +203,64 @@ __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const
     }
   };
 
-  // prologue: first D items of the first tile, rope values of its first chunk
-  static_for<0, D>([&](auto id) {
-    constexpr int d = decltype(id)::v;
-    prefetch((d / G) / 8, (d / G) % 8, d % G, d % D);
-  });
+  // prologue: first PD items (chunk 0, heads 0..PD-1), rope values of chunk 0
+  static_for<0, PD>([&](auto id) { constexpr int d = decltype(id)::v; fetch(wq[d], src_cur, ok_cur, 0, d); });
   float2 cs[8], csn[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { cs[k] = make_float2(0.f, 0.f); csn[k] = make_float2(0.f, 0.f); }
-  load_cs(cs, tile_first, 0);
+  load_cs(cs, tile_first * TT + tid, 0);
 
   for (int64_t tile = tile_first; tile < tile_end; ++tile) {
     const int64_t t = tile * TT + tid;
-    t_cur = t;
     const bool live = t < p.L;
+    const unsigned char* src_nxt = src_cur + TT * 4;
+    const bool ok_nxt = (t + TT) < t_limit;
     float2 acc[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) acc[g] = make_float2(0.f, 0.f);
 
     for (int a = 0; a < 8; ++a) {
       // rope values of the next chunk (next tile's chunk 0 after the last one) travel while this chunk computes
-      load_cs(csn, a == 7 ? tile + 1 : tile, (a + 1) & 7);
+      load_cs(csn, a == 7 ? t + TT : t, (a + 1) & 7);
+      // prefetch targets of this chunk's items: same chunk (hl+PD < G) or the next chunk / next tile's chunk 0
+      const unsigned char* src_w = (a == 7) ? src_nxt : src_cur;
+      const bool ok_w = (a == 7) ? ok_nxt : ok_cur;
+      const int a_w = (a + 1) & 7;
       static_for<0, G>([&](auto ig) {
         constexpr int hl = decltype(ig)::v;
-        cp_async_wait<D - 1>();  // this item's words have landed (one commit group per item)
         uint32_t w[NRW];
-        constexpr int slot = hl % D;   // G is a multiple of D, so item i lives in slot hl % D
 #pragma unroll
-        for (int i = 0; i < NRW; ++i) w[i] = lds_u32(ring0 + (uint32_t)(slot * NRW + i) * (TT * 4));
-        // item i+D re-uses this slot: its copies are issued only after w[] has been read into registers
-        // (lds_u32 is volatile and precedes the copy in program order; the words are consumed below)
-        {
-          constexpr int hn = (hl + D) % G;
-          constexpr int wrap = (hl + D) / G;  // 0 or 1: next chunk
-          const int an = a + wrap;
-          prefetch(an >> 3, an & 7, hn, slot);
-        }
-        if (live && hl < nh) k_item<BITS>(w, a, tab0 + (uint32_t)hl * (kHeadDim * N * 8) + (uint32_t)a * (8 * N * 8), cs, acc[hl]);
+        for (int i = 0; i < NRW; ++i) w[i] = wq[hl % PD][i];
+        if constexpr (hl + PD < G) fetch(wq[hl % PD], src_cur, ok_cur, a, hl + PD);
+        else fetch(wq[hl % PD], src_w, ok_w, a_w, hl + PD - G);
+        // no per-thread guard: lanes past L (and heads past nh) compute on zero / stale inputs and are dropped at the store
+        k_item<BITS>(w, a, tab0 + (uint32_t)hl * (kHeadDim * N * 8) + (uint32_t)a * (8 * N * 8), cs, acc[hl]);
       });
 #pragma unroll
       for (int k = 0; k < 8; ++k) cs[k] = csn[k];
     }
 
     // ---- write back: this thread owns column t of the score matrix for the CTA's heads ---------------------------
+    float old[G];
+#pragma unroll
+    for (int hl = 0; hl < G; ++hl) {
+      old[hl] = 0.f;
+      if (p.accumulate && live && hl < nh) old[hl] = p.out[(int64_t)(h0 + hl) * p.out_stride + t];
+    }
 #pragma unroll
     for (int hl = 0; hl < G; ++hl) {
       if (hl < nh) {
-        float s = acc[hl].x + acc[hl].y;
-        if (live) {
-          float* o = p.out + (int64_t)(h0 + hl) * p.out_stride + t;
-          if (p.accumulate) s += *o;   // legacy: mul += S;  sparse: the outlier pre-pass already deposited its part
-          s *= p.scale;
-          *o = s;
-        }
+        const float s = ((acc[hl].x + acc[hl].y) + old[hl]) * p.scale;
+        if (live) p.out[(int64_t)(h0 + hl) * p.out_stride + t] = s;
         if (p.gmax != nullptr) {
           const float m = warp_max(live ? s : -INFINITY);
           if ((tid & 31) == 0 && m > -INFINITY) atomic_max_float(p.gmax + h0 + hl, m);
         }
       }
     }
+    src_cur = src_nxt;
+    ok_cur = ok_nxt;
   }
-  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -615,10 +618,12 @@ __global__ void rope_table_kernel(float2* __restrict__ out, float rope_theta, in
 template <int BITS>
 static int launch_k_scores(const KParams& p, cudaStream_t st) {
   using C = KCfg<BITS>;
-  const size_t smem = 256 + (size_t)C::G * kHeadDim * C::N * sizeof(float2) + (size_t)C::G * kHeadDim * 4 + (size_t)C::D * C::NRW * C::TT * 4;
+  const size_t smem = 256 + (size_t)C::G * kHeadDim * C::N * sizeof(float2) + (size_t)C::G * kHeadDim * 4;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_scores_kernel<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_scores_kernel<BITS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_scores_kernel<BITS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
@@ -632,7 +637,8 @@ static int launch_k_scores(const KParams& p, cudaStream_t st) {
   q.tiles_per_cta = (int)((n_tiles + max_splits - 1) / max_splits);
   const int64_t splits = (n_tiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
   const dim3 grid((unsigned)splits, (unsigned)n_groups);
-  k_scores_kernel<BITS><<<grid, C::kThreads, smem, st>>>(q);
+  if (p.H % C::G == 0) k_scores_kernel<BITS, true><<<grid, C::kThreads, smem, st>>>(q);
+  else k_scores_kernel<BITS, false><<<grid, C::kThreads, smem, st>>>(q);
   KVQ_LAUNCH_CHECK();
   return 0;
 }

@@ -352,15 +352,27 @@ __global__ void attend_init_kernel(const float* __restrict__ q, const __half* __
 }
 
 // out[h,c] = (sum_s o[s,h,c] + sum_i p_i * sink_v[h,i,c]) / (sum_s l[s,h] + sum_i p_i),  p_i = exp(sink_s[h,i]-max)
-__global__ void attend_combine_kernel(const float* __restrict__ po, const float* __restrict__ pl, int n_part, int H,
-                                      const float* __restrict__ gmax, const float* __restrict__ sink_scores,
-                                      const __half* __restrict__ sink_v, int n_sink, float* __restrict__ out) {
-  const int h = blockIdx.x, c = threadIdx.x;  // blockDim = 128
+// grid = H, block = 1024: 8 slices of the partials x 128 channels, reduced through shared memory
+__global__ void __launch_bounds__(1024) attend_combine_kernel(const float* __restrict__ po, const float* __restrict__ pl,
+                                                              int n_part, int H, const float* __restrict__ gmax,
+                                                              const float* __restrict__ sink_scores,
+                                                              const __half* __restrict__ sink_v, int n_sink,
+                                                              float* __restrict__ out) {
+  __shared__ float s_o[8][kHeadDim];
+  __shared__ float s_l[8];
+  const int h = blockIdx.x, c = threadIdx.x & (kHeadDim - 1), g = threadIdx.x >> 7;
   float o = 0.f, l = 0.f;
-  for (int s = 0; s < n_part; ++s) {
+  for (int s = g; s < n_part; s += 8) {
     o += po[((int64_t)s * H + h) * kHeadDim + c];
-    l += pl[(int64_t)s * H + h];
+    if (c == 0) l += pl[(int64_t)s * H + h];
   }
+  s_o[g][c] = o;
+  if (c == 0) s_l[g] = l;
+  __syncthreads();
+  if (g != 0) return;
+  o = 0.f; l = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { o += s_o[i][c]; l += s_l[i]; }
   const float m = gmax[h];
   for (int i = 0; i < n_sink; ++i) {
     const float pi = __expf(sink_scores[h * 64 + i] - m);
@@ -552,7 +564,7 @@ int kvq_attend(int bits, const float* q, const int32_t* kcache, const float* klu
     }
     if (rc) return rc;
   }
-  attend_combine_kernel<<<H, kHeadDim, 0, st>>>(part_o, part_l, n_cta, H, gmax, sink_scores,
+  attend_combine_kernel<<<H, 1024, 0, st>>>(part_o, part_l, n_cta, H, gmax, sink_scores,
                                                 static_cast<const __half*>(sink_v), n_sink, out);
   KVQ_LAUNCH_CHECK();
   return 0;

@@ -4,6 +4,7 @@ cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q --tb=short > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -15 gpurun_out/pytest_gpu.log
+timeout 300 python tests/golden/gen_refcuda_golden.py > gpurun_out/gen_refcuda.log 2>&1; tail -3 gpurun_out/gen_refcuda.log
 rm -f gpurun_out/probe.jsonl
 PROBE_BITS=${PROBE_BITS:-4,3} PROBE_L=${PROBE_L:-131072} timeout 600 python scripts/gpu_probe.py > gpurun_out/probe.log 2>&1; echo "probe rc=$?" >> gpurun_out/probe.log
 grep -E '"impl": "ours"|rc=|Error|error' gpurun_out/probe.log | tail -20
