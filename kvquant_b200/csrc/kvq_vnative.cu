@@ -19,10 +19,10 @@
 
 namespace kvq {
 
-constexpr int kNThreads = 1024;     // 32 warps: two threads per packed word row, each takes 16 of a tile's 32 tokens
+constexpr int kNThreads = 512;
 constexpr int kNT = 32;          // tokens per stage (128-byte rows, 128B swizzle)
 constexpr int kNMaxStages = 3;
-constexpr int kNTokPerWarp = kNT / (kNThreads / 32);   // outlier rows handled by one warp per tile (1)
+constexpr int kNTokPerWarp = kNT / (kNThreads / 32);   // outlier rows handled by one warp per tile (2)
 
 struct VNParams {
   const float* score;        // [H, score_stride] scaled scores
@@ -74,9 +74,9 @@ __device__ __forceinline__ void ffma2v(float2& acc, const float2 a, const float2
 template <int BITS, int SUB>
 __device__ __forceinline__ void vn_tile_unit(const unsigned char* stage, uint32_t row_off, uint32_t swz,
                                              uint32_t row_off2, uint32_t swz2, int part, uint32_t tab,
-                                             const float* __restrict__ wsrow, float2* __restrict__ acc, const int q0) {
+                                             const float* __restrict__ wsrow, float2* __restrict__ acc) {
 #pragma unroll 2
-  for (int q = q0; q < q0 + 4; ++q) {   // 16 tokens: this thread's half of the tile
+  for (int q = 0; q < 8; ++q) {
     const uint4 wa = *reinterpret_cast<const uint4*>(stage + row_off + ((q ^ swz) << 4));
     uint4 wb = make_uint4(0, 0, 0, 0);
     if constexpr (BITS == 3 && SUB < 2) wb = *reinterpret_cast<const uint4*>(stage + row_off2 + ((q ^ swz2) << 4));
@@ -140,33 +140,28 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
   const uint32_t tab = smem_u32(s_tab) + lane * 8;
 
   // ---- thread -> unit mapping (same as kvq_vaccum.cu) ------------------------------------------------------------
-  // unit = (packed word row [or half row for 2-bit, sub-row role for 3-bit], token half): up to 2 units per thread
-  int u_row[2], u_head[2], u_ch0[2], u_part[2], u_q0[2];
+  int u_row[2], u_head[2], u_ch0[2], u_part[2];
   bool u_on[2];
   int sub = 0;
   if constexpr (BITS == 3) {
     sub = warp % 3;
-    const int tri = warp / 3;            // 10 full warp-triples in 32 warps (warps 30, 31 idle)
+    const int tri = warp / 3;
     const int ngroups = p.H * 4;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const int ug = tri * 32 + lane + i * 320;
-      const int half = ug / ngroups, gi = ug - half * ngroups;
-      u_on[i] = (warp < 30) && ug < 2 * ngroups;
+      const int gi = tri * 32 + lane + i * 160;
+      u_on[i] = (warp < 15) && gi < ngroups;
       u_row[i] = 3 * gi + sub;
       u_head[i] = gi >> 2;
       u_ch0[i] = (gi & 3) * 32 + (sub == 0 ? 0 : (sub == 1 ? 11 : 22));
       u_part[i] = 0;
-      u_q0[i] = 4 * half;
     }
   } else {
     const int nunits = p.H * 16;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const int uu = tid + i * kNThreads;
-      const int half = uu / nunits, u = uu - half * nunits;
-      u_on[i] = uu < 2 * nunits;
-      u_q0[i] = 4 * half;
+      const int u = tid + i * kNThreads;
+      u_on[i] = u < nunits;
       if constexpr (BITS == 4) { u_row[i] = u; u_part[i] = 0; u_head[i] = u >> 4; u_ch0[i] = (u & 15) * 8; }
       else { u_row[i] = u >> 1; u_part[i] = u & 1; u_head[i] = u >> 4; u_ch0[i] = ((u >> 1) & 7) * 16 + (u & 1) * 8; }
     }
@@ -210,7 +205,7 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
   };
   // weights: H*32 (head, token) values per tile -> 2 per thread at H = 32 (up to 4 at H = 64)
   const int n_w = p.H * kNT;
-  constexpr int NW = 2;   // H*32 values per tile over 1024 threads (H <= 64)
+  constexpr int NW = 4;
   float wpre[NW], wspre[NW], offpre[NW];
   float lacc[NW], oacc_off[NW];
 #pragma unroll
@@ -295,11 +290,11 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
       if (u_on[i]) {
         const float* wsrow = wsbuf + u_head[i] * kNT;
         if constexpr (BITS == 3) {
-          if (sub == 0) vn_tile_unit<3, 0>(stage, r_off[i], r_swz[i], r_off2[i], r_swz2[i], 0, tab, wsrow, acc[i], u_q0[i]);
-          else if (sub == 1) vn_tile_unit<3, 1>(stage, r_off[i], r_swz[i], r_off2[i], r_swz2[i], 0, tab, wsrow, acc[i], u_q0[i]);
-          else vn_tile_unit<3, 2>(stage, r_off[i], r_swz[i], r_off2[i], r_swz2[i], 0, tab, wsrow, acc[i], u_q0[i]);
+          if (sub == 0) vn_tile_unit<3, 0>(stage, r_off[i], r_swz[i], r_off2[i], r_swz2[i], 0, tab, wsrow, acc[i]);
+          else if (sub == 1) vn_tile_unit<3, 1>(stage, r_off[i], r_swz[i], r_off2[i], r_swz2[i], 0, tab, wsrow, acc[i]);
+          else vn_tile_unit<3, 2>(stage, r_off[i], r_swz[i], r_off2[i], r_swz2[i], 0, tab, wsrow, acc[i]);
         } else {
-          vn_tile_unit<BITS, 0>(stage, r_off[i], r_swz[i], 0, 0, u_part[i], tab, wsrow, acc[i], u_q0[i]);
+          vn_tile_unit<BITS, 0>(stage, r_off[i], r_swz[i], 0, 0, u_part[i], tab, wsrow, acc[i]);
         }
       }
     }
@@ -344,23 +339,22 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
   }
   __syncthreads();
   for (int i = tid; i < p.H; i += kNThreads) p.out_l[(int64_t)blockIdx.x * p.H + i] = s_l[i];
-  // the two token-halves of a row (and the outlier stream) meet in the shared accumulator
+  float* obase = p.out_o + (int64_t)blockIdx.x * hidden;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     if (u_on[i]) {
+      const float hoff = s_off[u_head[i]];
       const int nch = (BITS == 3) ? (sub == 2 ? 10 : 11) : 8;
 #pragma unroll
       for (int k = 0; k < 2 * NP; ++k) {
         if (k < nch) {
           const int j = u_head[i] * kHeadDim + u_ch0[i] + k;
-          atomicAdd(&s_oacc[j], (k & 1) ? acc[i][k >> 1].y : acc[i][k >> 1].x);
+          const float v = (k & 1) ? acc[i][k >> 1].y : acc[i][k >> 1].x;
+          obase[j] = v + hoff + s_oacc[j];
         }
       }
     }
   }
-  __syncthreads();
-  float* obase = p.out_o + (int64_t)blockIdx.x * hidden;
-  for (int j = tid; j < hidden; j += kNThreads) obase[j] = s_oacc[j] + s_off[j >> 7];
 }
 
 constexpr uint32_t kVNSmemBudget = 227u * 1024u;
