@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-profile", default="", help="write a per-kernel table of 3 graph replays to this file (diagnostic)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -269,6 +270,15 @@ def main():
 
     for i in range(args.warmup):
         step_device()
+    if args.torch_profile and rank == 0:
+        from torch.profiler import profile, ProfilerActivity
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(3):
+                step_device()
+            torch.cuda.synchronize()
+        with open(args.torch_profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

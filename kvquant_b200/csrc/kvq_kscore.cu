@@ -139,7 +139,7 @@ template <int BITS, bool FULL>
 __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const KParams p) {
   using C = KCfg<BITS>;
   constexpr int N = C::N, W = C::W, G = C::G, TT = C::TT, NRW = C::NRW;
-  constexpr int PD = 4;   // register prefetch distance in work items (G % PD == 0)
+  constexpr int PD = (BITS == 4) ? 8 : 4;   // register prefetch distance in work items (G % PD == 0)
   extern __shared__ unsigned char smem_raw[];
   // table base must be 256-byte aligned (the low address byte carries code*8)
   unsigned char* smem = smem_raw + ((256u - (smem_u32(smem_raw) & 255u)) & 255u);
@@ -526,7 +526,7 @@ static int launch_k_kappa(const KParams& p, cudaStream_t st) {
 // store_all = 0: only heads with outliers are touched, out += contribution (legacy accumulate semantics).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kOutThreads = 256;
-constexpr int kOutBatch = 14;   // (value, index) pairs fetched per thread before they are consumed
+constexpr int kOutSplit = 4;   // threads per token: each owns H/4 consecutive heads (the row is sorted by channel)
 
 __global__ void __launch_bounds__(kOutThreads) k_outlier_kernel(
     const float* __restrict__ q, const float* __restrict__ outliers, const int32_t* __restrict__ outlier_idx,
@@ -542,13 +542,19 @@ __global__ void __launch_bounds__(kOutThreads) k_outlier_kernel(
     s_theta[tid] = powf(rope_theta, (-2 * __int2float_rd(tid % (headdim / 2)) / headdim));  // DK.cu:504
   }
   __syncthreads();
-  const int64_t t = (int64_t)blockIdx.x * kOutThreads + tid;
+  // consecutive lanes = consecutive tokens of the same head range (coalesced score writes)
+  constexpr int TPB = kOutThreads / kOutSplit;   // tokens per block
+  const int part = tid / TPB;                    // which quarter of the heads
+  const int64_t t = (int64_t)blockIdx.x * TPB + (tid - part * TPB);
   if (t >= L) return;
+  const int hpp = (H + kOutSplit - 1) / kOutSplit;
+  const int h_lo = part * hpp, h_hi = min(H, h_lo + hpp);
+  const int c_lo = h_lo * kHeadDim, c_hi = h_hi * kHeadDim;
   const int pos = (int)t + pos_offset;
-  const float* vrow = outliers + t * n_out;     // the thread reads its own 2 x n_out x 4 bytes; every fetched sector
-  const int32_t* irow = outlier_idx + t * n_out;  // is consumed completely (L1 keeps it between the batches)
+  const float* vrow = outliers + t * n_out;
+  const int32_t* irow = outlier_idx + t * n_out;
   float* ocol = out + t;
-  int next_h = 0;       // store_all: next head that still has to be written
+  int next_h = h_lo;    // store_all: next head of this range that still has to be written
   int cur_h = -1;
   float acc = 0.f;
   auto flush = [&]() {
@@ -562,18 +568,18 @@ __global__ void __launch_bounds__(kOutThreads) k_outlier_kernel(
       }
     }
   };
-  for (int k0 = 0; k0 < n_out; k0 += kOutBatch) {
-    float v[kOutBatch];
-    int ci[kOutBatch];
+  // every thread scans the row's channel indices (cheap, L1-resident after the first quarter's pass) and evaluates
+  // only the entries of its own head range
+  for (int k0 = 0; k0 < n_out; k0 += 8) {
+    int ci[8];
 #pragma unroll
-    for (int u = 0; u < kOutBatch; ++u) {
-      const bool in = k0 + u < n_out;
-      v[u] = in ? __ldg(vrow + k0 + u) : 0.f;
-      ci[u] = in ? __ldg(irow + k0 + u) : 0;
-    }
+    for (int u = 0; u < 8; ++u) ci[u] = (k0 + u < n_out) ? __ldg(irow + k0 + u) : 0x7fffffff;
+    float v[8];
 #pragma unroll
-    for (int u = 0; u < kOutBatch; ++u) {
-      if (v[u] == 0.f) continue;  // pads / non-outliers contribute exactly 0 in the reference too
+    for (int u = 0; u < 8; ++u) v[u] = (ci[u] >= c_lo && ci[u] < c_hi) ? __ldg(vrow + k0 + u) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (v[u] == 0.f) continue;  // not ours, or a pad / non-outlier (contributes exactly 0 in the reference too)
       const int col = ci[u];
       const int h = col >> 7, c = col & (kHeadDim - 1);
       if (h != cur_h) { flush(); cur_h = h; acc = 0.f; }
@@ -588,13 +594,14 @@ __global__ void __launch_bounds__(kOutThreads) k_outlier_kernel(
   }
   flush();
   if (store_all)
-    for (; next_h < H; ++next_h) ocol[(int64_t)next_h * out_stride] = 0.f;
+    for (; next_h < h_hi; ++next_h) ocol[(int64_t)next_h * out_stride] = 0.f;
 }
 
 static int launch_k_outliers(const KParams& p, float rope_theta, int store_all, cudaStream_t st) {
   const size_t smem = (size_t)p.H * kHeadDim * 4 + kHalf * 4;
   if (smem > 48 * 1024) return KVQ_E_UNSUPPORTED;
-  const unsigned grid = (unsigned)((p.L + kOutThreads - 1) / kOutThreads);
+  constexpr int TPB = kOutThreads / kOutSplit;
+  const unsigned grid = (unsigned)((p.L + TPB - 1) / TPB);
   k_outlier_kernel<<<grid, kOutThreads, smem, st>>>(p.q, p.outliers, p.outlier_idx, p.out, p.out_stride, p.L, p.H,
                                                     p.n_out, rope_theta, p.pos_offset, store_all);
   KVQ_LAUNCH_CHECK();

@@ -11,7 +11,7 @@ grep -E '"impl": "ours"|rc=|Error|error' gpurun_out/probe.log | tail -20
 KVQ_K_IMPL=kappa PROBE_TAG=kappa PROBE_SKIP_REF=1 PROBE_BITS=${PROBE_BITS:-4,3} PROBE_L=${PROBE_L:-131072} timeout 600 python scripts/gpu_probe.py > gpurun_out/probe_kappa.log 2>&1
 grep -E '"op": "k_opt' gpurun_out/probe_kappa.log | tail -8
 if [ "${RUN_BENCH:-1}" = "1" ]; then
-  timeout 900 python bench.py --steps 10 --warmup 3 ${BENCH_ARGS} > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
+  timeout 900 python bench.py --steps 10 --warmup 3 --torch-profile gpurun_out/step_kernels.txt ${BENCH_ARGS} > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
   tail -3 gpurun_out/bench.log; tail -5 gpurun_out/bench.err
 fi
 if [ "${RUN_NCU:-1}" = "1" ]; then
