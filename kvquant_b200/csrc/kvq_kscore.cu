@@ -526,84 +526,58 @@ static int launch_k_kappa(const KParams& p, cudaStream_t st) {
 // store_all = 0: only heads with outliers are touched, out += contribution (legacy accumulate semantics).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kOutThreads = 256;
-constexpr int kOutSplit = 4;   // threads per token: each owns H/4 consecutive heads (the row is sorted by channel)
 
+// thread = one (token, outlier slot) entry.  cos/sin come from the RoPE table (bit-identical to the reference's
+// cosf/sinf(theta*pos)); entries of one (token, head) are adjacent (rows are sorted by channel), so a warp-level
+// segmented sum leaves ~1 atomic per (token, head) instead of the reference's one per entry.
 __global__ void __launch_bounds__(kOutThreads) k_outlier_kernel(
     const float* __restrict__ q, const float* __restrict__ outliers, const int32_t* __restrict__ outlier_idx,
-    float* __restrict__ out, int64_t out_stride, int64_t L, int H, int n_out, float rope_theta, int pos_offset,
-    int store_all) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* s_q = reinterpret_cast<float*>(smem_raw);            // [H*128]
-  float* s_theta = s_q + H * kHeadDim;                         // [64]
-  const int tid = threadIdx.x;
-  for (int i = tid; i < H * kHeadDim; i += kOutThreads) s_q[i] = q[i];
-  if (tid < kHalf) {
-    const int headdim = kHeadDim;
-    s_theta[tid] = powf(rope_theta, (-2 * __int2float_rd(tid % (headdim / 2)) / headdim));  // DK.cu:504
-  }
-  __syncthreads();
-  // consecutive lanes = consecutive tokens of the same head range (coalesced score writes)
-  constexpr int TPB = kOutThreads / kOutSplit;   // tokens per block
-  const int part = tid / TPB;                    // which quarter of the heads
-  const int64_t t = (int64_t)blockIdx.x * TPB + (tid - part * TPB);
-  if (t >= L) return;
-  const int hpp = (H + kOutSplit - 1) / kOutSplit;
-  const int h_lo = part * hpp, h_hi = min(H, h_lo + hpp);
-  const int c_lo = h_lo * kHeadDim, c_hi = h_hi * kHeadDim;
-  const int pos = (int)t + pos_offset;
-  const float* vrow = outliers + t * n_out;
-  const int32_t* irow = outlier_idx + t * n_out;
-  float* ocol = out + t;
-  int next_h = h_lo;    // store_all: next head of this range that still has to be written
-  int cur_h = -1;
-  float acc = 0.f;
-  auto flush = [&]() {
-    if (cur_h >= 0) {
-      if (store_all) {
-        for (; next_h < cur_h; ++next_h) ocol[(int64_t)next_h * out_stride] = 0.f;
-        ocol[(int64_t)cur_h * out_stride] = acc;
-        next_h = cur_h + 1;
-      } else {
-        ocol[(int64_t)cur_h * out_stride] += acc;
-      }
-    }
-  };
-  // every thread scans the row's channel indices (cheap, L1-resident after the first quarter's pass) and evaluates
-  // only the entries of its own head range
-  for (int k0 = 0; k0 < n_out; k0 += 8) {
-    int ci[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) ci[u] = (k0 + u < n_out) ? __ldg(irow + k0 + u) : 0x7fffffff;
-    float v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = (ci[u] >= c_lo && ci[u] < c_hi) ? __ldg(vrow + k0 + u) : 0.f;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (v[u] == 0.f) continue;  // not ours, or a pad / non-outlier (contributes exactly 0 in the reference too)
-      const int col = ci[u];
-      const int h = col >> 7, c = col & (kHeadDim - 1);
-      if (h != cur_h) { flush(); cur_h = h; acc = 0.f; }
-      const float theta = s_theta[c & (kHalf - 1)];
+    float* __restrict__ out, int64_t out_stride, int64_t L, int H, int n_out, const float2* __restrict__ rope,
+    int64_t rope_npos, int pos_offset, float scale) {
+  const int64_t e = (int64_t)blockIdx.x * kOutThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t total = L * n_out;
+  float contrib = 0.f;
+  int64_t key = -1 - lane;   // unique negative keys for idle lanes (never merge)
+  int64_t t = 0;
+  int h = 0;
+  if (e < total) {
+    t = e / n_out;
+    const float v = outliers[e];
+    const int col = outlier_idx[e];
+    h = col >> 7;
+    const int c = col & (kHeadDim - 1);
+    key = t * 64 + h;
+    if (v != 0.f) {   // pads / non-outliers contribute exactly 0 in the reference too
+      const float2 cs = rope[(int64_t)(c & (kHalf - 1)) * rope_npos + t + pos_offset];
       const float sign = (c < kHalf) ? 1.f : -1.f;
-      float sn, cs;
-      sincosf(theta * pos, &sn, &cs);           // same libdevice range reduction as the reference's cosf / sinf
-      float dot = v[u] * cs * s_q[col];
-      dot += sign * v[u] * sn * s_q[col ^ kHalf];
-      acc += dot;
+      float dot = v * cs.x * __ldg(q + col);            // same operation order as DK.cu:513-515
+      dot += sign * v * cs.y * __ldg(q + (col ^ kHalf));
+      contrib = dot * scale;
     }
   }
-  flush();
-  if (store_all)
-    for (; next_h < h_hi; ++next_h) ocol[(int64_t)next_h * out_stride] = 0.f;
+  // segmented sum over runs of equal keys (runs are contiguous in lane order)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float v2 = __shfl_down_sync(0xffffffffu, contrib, o);
+    const int64_t k2 = __shfl_down_sync(0xffffffffu, key, o);
+    if (lane + o < 32 && k2 == key) contrib += v2;
+  }
+  const int64_t kprev = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool leader = (lane == 0) || (kprev != key);
+  if (leader && e < total && contrib != 0.f) atomicAdd(out + (int64_t)h * out_stride + t, contrib);
 }
 
-static int launch_k_outliers(const KParams& p, float rope_theta, int store_all, cudaStream_t st) {
-  const size_t smem = (size_t)p.H * kHeadDim * 4 + kHalf * 4;
-  if (smem > 48 * 1024) return KVQ_E_UNSUPPORTED;
-  constexpr int TPB = kOutThreads / kOutSplit;
-  const unsigned grid = (unsigned)((p.L + TPB - 1) / TPB);
-  k_outlier_kernel<<<grid, kOutThreads, smem, st>>>(p.q, p.outliers, p.outlier_idx, p.out, p.out_stride, p.L, p.H,
-                                                    p.n_out, rope_theta, p.pos_offset, store_all);
+// zero_first = 1: `out` is a fresh score buffer (fused path) and is cleared before the scatter
+static int launch_k_outliers(const KParams& p, int zero_first, float scale, cudaStream_t st) {
+  if (zero_first) {
+    cudaError_t e = cudaMemsetAsync(p.out, 0, sizeof(float) * (size_t)p.H * (size_t)p.out_stride, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int64_t total = p.L * p.n_out;
+  const unsigned grid = (unsigned)((total + kOutThreads - 1) / kOutThreads);
+  k_outlier_kernel<<<grid, kOutThreads, 0, st>>>(p.q, p.outliers, p.outlier_idx, p.out, p.out_stride, p.L, p.H,
+                                                 p.n_out, p.rope, p.rope_npos, p.pos_offset, scale);
   KVQ_LAUNCH_CHECK();
   return 0;
 }
@@ -685,7 +659,8 @@ int k_scores_fused(int bits, const float* q, const int32_t* cache, float* scores
   p.gmax = gmax; p.Lmax = Lmax; p.L = L; p.out_stride = score_stride; p.rope_npos = rope_npos;
   p.H = H; p.n_out = n_out; p.pos_offset = pos_offset; p.scale = scale; p.accumulate = 0;
   if (outliers != nullptr) {
-    const int rc = launch_k_outliers(p, theta, /*store_all=*/1, st);  // initialises the score buffer
+    // outlier contributions are deposited UNSCALED (the dense kernel applies `scale` to out + S)
+    const int rc = launch_k_outliers(p, /*zero_first=*/1, 1.f, st);
     if (rc != 0) return rc;
     p.accumulate = 1;
   }
@@ -730,7 +705,7 @@ int kvq_k_matvec(int bits, const float* q, const int32_t* cache, float* mul, con
     p.H = H; p.n_out = n_out; p.pos_offset = pos_offset;
     p.scale = 1.f; p.accumulate = 1;
     if (outliers != nullptr) {
-      const int rc0 = launch_k_outliers(p, theta, /*store_all=*/0, static_cast<cudaStream_t>(stream));
+      const int rc0 = launch_k_outliers(p, /*zero_first=*/0, 1.f, static_cast<cudaStream_t>(stream));
       if (rc0 != 0) return rc0;
     }
     const int rc = k_scores_dispatch(bits, p, static_cast<cudaStream_t>(stream));

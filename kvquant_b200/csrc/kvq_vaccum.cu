@@ -335,20 +335,26 @@ __global__ void __launch_bounds__(kVThreads, 1) v_accum_kernel(const __grid_cons
 // sink scores (fp16 post-RoPE keys, modeling_llama.py:1948-1949) and the initial per-head max
 __global__ void attend_init_kernel(const float* __restrict__ q, const __half* __restrict__ sink_k, int n_sink,
                                    float* __restrict__ sink_scores, float* __restrict__ gmax, float scale) {
-  const int h = blockIdx.x, i = threadIdx.x;  // blockDim = 64
-  float s = -INFINITY;
-  if (i < n_sink) {
-    float a = 0.f;
-    for (int c = 0; c < kHeadDim; ++c)
-      a = fmaf(q[h * kHeadDim + c], __half2float(sink_k[((int64_t)h * kHeadDim + c) * n_sink + i]), a);
-    s = a * scale;
-    sink_scores[h * 64 + i] = s;
+  // grid = H, block = 128 (thread = channel): s_i = scale * sum_c q[h,c] * sink_k[h,c,i], reduced per sink
+  const int h = blockIdx.x, c = threadIdx.x;
+  __shared__ float s_part[4];
+  __shared__ float s_max;
+  if (c == 0) s_max = -INFINITY;
+  const float qc = q[h * kHeadDim + c];
+  for (int i = 0; i < n_sink; ++i) {
+    float v = qc * __half2float(sink_k[((int64_t)h * kHeadDim + c) * n_sink + i]);
+    v = warp_sum(v);
+    __syncthreads();
+    if ((c & 31) == 0) s_part[c >> 5] = v;
+    __syncthreads();
+    if (c == 0) {
+      const float s = (s_part[0] + s_part[1] + s_part[2] + s_part[3]) * scale;
+      sink_scores[h * 64 + i] = s;
+      s_max = fmaxf(s_max, s);
+    }
   }
-  float m = warp_max(s);
-  __shared__ float sm[2];
-  if ((i & 31) == 0) sm[i >> 5] = m;
   __syncthreads();
-  if (i == 0) gmax[h] = fmaxf(sm[0], sm[1]);
+  if (c == 0) gmax[h] = s_max;
 }
 
 // out[h,c] = (sum_s o[s,h,c] + sum_i p_i * sink_v[h,i,c]) / (sum_s l[s,h] + sum_i p_i),  p_i = exp(sink_s[h,i]-max)
@@ -545,7 +551,7 @@ int kvq_attend(int bits, const float* q, const int32_t* kcache, const float* klu
   float* part_o = sink_scores + (int64_t)H * 64;
   float* part_l = part_o + (int64_t)kMaxPart * H * kHeadDim;
   const float scale = 0.08838834764831845f;  // 1/sqrt(128)  (modeling_llama.py:1959,1973)
-  attend_init_kernel<<<H, 64, 0, st>>>(q, static_cast<const __half*>(sink_k), n_sink, sink_scores, gmax, scale);
+  attend_init_kernel<<<H, kHeadDim, 0, st>>>(q, static_cast<const __half*>(sink_k), n_sink, sink_scores, gmax, scale);
   KVQ_LAUNCH_CHECK();
   int n_cta = 0;
   if (L > 0) {
