@@ -139,14 +139,16 @@ KVQ_API int kvq_attend(int bits, const float* q,
  *   smallest normalised values, V thresholds are the (n_each+1)-th order statistics.
  *   klut_sub: LUT used for the K end-entry subtraction (lookup_table2 under Q-Norm), may equal klut.
  *   v_cent: f32 [2^bits] sorted centroids; vlut_tok row `slot` is WRITTEN; v_aff (optional, f32 [Lmax,2]) row
- *   `slot` receives (sf, off).
+ *   `slot` receives (sf, off); v_cent_deq (optional): Q-Norm centroids cent*normscale+normoffset -- the outlier
+ *   residual is taken against LUT2_t[zp] = v_cent_deq[zp]*sf+off (modeling_llama.py:1115-1118,1149-1152).
  *   Cache words at `slot` are OVERWRITTEN (not added).  Outlier rows (f32/i32 [Lmax, 2*n_each]) row `slot` written.
  * ------------------------------------------------------------------------------------------------------------- */
 KVQ_API int kvq_append_kv_fused(int bits, int H, int64_t Lmax, int64_t slot, int n_each,
                         const float* k_new, int32_t* kcache, const float* klut, const float* klut_sub,
                         const float* k_thr_lower, const float* k_thr_upper,
                         float* k_outliers, int32_t* k_outlier_idx,
-                        const float* v_new, int32_t* vcache, const float* v_cent, float* vlut_tok, float* v_aff,
+                        const float* v_new, int32_t* vcache, const float* v_cent, const float* v_cent_deq,
+                        float* vlut_tok, float* v_aff,
                         float* v_outliers, int32_t* v_outlier_idx,
                         void* stream);
 

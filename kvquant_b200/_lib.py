@@ -34,7 +34,7 @@ SIGNATURES = {
     "kvq_attend": (_c_int, [_c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_i64, _c_i64, _p,
                             _c_i64, _c_f, _c_int, _p, _p, _c_int, _p, _p, _p]),
     "kvq_append_kv_fused": (_c_int, [_c_int, _c_int, _c_i64, _c_i64, _c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
-                                     _p, _p, _p, _p, _p, _p]),
+                                     _p, _p, _p, _p, _p, _p, _p]),
     "kvq_k_spmv_csr": (_c_int, [_p, _p, _p, _p, _p, _p, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_f, _c_int, _p]),
     "kvq_v_spmv_csc": (_c_int, [_p, _p, _p, _p, _p, _p, _c_int, _c_i64, _c_int, _c_int, _c_int, _p]),
     "kvq_append_k_orig": (_c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_i64, _c_i64, _p]),

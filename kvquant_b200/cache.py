@@ -51,7 +51,7 @@ class LayerCache:
     """Native quantised K+V cache of one layer (reference-compatible tensor layouts)."""
 
     def __init__(self, bits, num_heads, max_len, klut, klut_sub, thr_lower, thr_upper, v_cent, device,
-                 include_sparse=True, sparsity_threshold=0.99, n_sink=0):
+                 include_sparse=True, sparsity_threshold=0.99, n_sink=0, v_norm=None):
         self.lib = _lib.load()
         self.bits, self.H, self.Lmax = int(bits), int(num_heads), int(max_len)
         if self.Lmax % 4:
@@ -66,9 +66,15 @@ class LayerCache:
         self.kcache = torch.zeros((self.H, W, self.Lmax), dtype=torch.int32, device=dev)
         self.vcache = torch.zeros((self.H, W, self.Lmax), dtype=torch.int32, device=dev)
         self.klut = klut.contiguous()
+        # Q-Norm (ML.py:485-488): codes are chosen against LUT, dequantisation and the outlier end-entry subtraction
+        # use LUT2 = (cent*normscale+normoffset)*range + zp
         self.klut_sub = (klut_sub if klut_sub is not None else klut).contiguous()
+        self.klut_deq = self.klut_sub
         self.thr_lower, self.thr_upper = thr_lower.contiguous(), thr_upper.contiguous()
         self.v_cent = v_cent.contiguous()
+        # V Q-Norm (ML.py:1115-1118): LUT2_t = (cent*ns+no)*sf_t + off_t -> same affine form with shifted centroids
+        self.v_cent_deq = self.v_cent if v_norm is None else (self.v_cent * float(v_norm[0]) + float(v_norm[1])).contiguous()
+        self.v_norm = v_norm
         self.vlut = torch.zeros((self.Lmax, 2 ** bits), dtype=torch.float32, device=dev)
         # per-token affine map (sf_t, off_t): LUT_t = v_cent*sf_t + off_t  -- what the native V kernel consumes
         self.vaff = torch.zeros((self.Lmax, 2), dtype=torch.float32, device=dev)
@@ -85,7 +91,7 @@ class LayerCache:
 
     @classmethod
     def from_luts(cls, bits, num_heads, max_len, klut, v_cent, device="cuda", include_sparse=True,
-                  sparsity_threshold=0.99, n_sink=0):
+                  sparsity_threshold=0.99, n_sink=0, v_norm=None):
         """klut: mapping with 'lut' [hidden, n] (and optional 'lut2'), 'thr_lower', 'thr_upper' (numpy or torch)."""
         def t(x):
             return torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(device).float().contiguous()
@@ -93,7 +99,7 @@ class LayerCache:
         lut2 = t(klut["lut2"]).view(num_heads * HEAD_DIM, -1) if klut.get("lut2") is not None else None
         return cls(bits, num_heads, max_len, lut, lut2, t(klut["thr_lower"]), t(klut["thr_upper"]),
                    t(np.sort(np.asarray(v_cent.cpu() if torch.is_tensor(v_cent) else v_cent).ravel())), device,
-                   include_sparse, sparsity_threshold, n_sink)
+                   include_sparse, sparsity_threshold, n_sink, v_norm)
 
     def reset(self):
         self.len = 0
@@ -137,7 +143,7 @@ class LayerCache:
             qc._f32(k_new, "k_new"), self.kcache.data_ptr(), self.klut.data_ptr(), self.klut_sub.data_ptr(),
             self.thr_lower.data_ptr(), self.thr_upper.data_ptr(), self.k_outliers.data_ptr(),
             self.k_outlier_idx.data_ptr(), qc._f32(v_new, "v_new"), self.vcache.data_ptr(), self.v_cent.data_ptr(),
-            self.vlut.data_ptr(), self.vaff.data_ptr(), self.v_outliers.data_ptr(), self.v_outlier_idx.data_ptr(), s),
+            self.v_cent_deq.data_ptr() if self.v_norm is not None else None, self.vlut.data_ptr(), self.vaff.data_ptr(), self.v_outliers.data_ptr(), self.v_outlier_idx.data_ptr(), s),
             "kvq_append_kv_fused")
         self.len += 1
 
@@ -153,10 +159,10 @@ class LayerCache:
         sp = self.include_sparse
         ns = self.n_sink if self.sink_k is not None else 0
         _lib.check(self.lib.kvq_attend(
-            self.bits, qc._f32(q, "q"), self.kcache.data_ptr(), self.klut.data_ptr(),
+            self.bits, qc._f32(q, "q"), self.kcache.data_ptr(), self.klut_deq.data_ptr(),
             self.k_outliers.data_ptr() if sp else None, self.k_outlier_idx.data_ptr() if sp else None,
             self.vcache.data_ptr(), self.vlut.data_ptr(),
-            self.v_cent.data_ptr() if self.use_native_v else None, self.vaff.data_ptr() if self.use_native_v else None,
+            self.v_cent_deq.data_ptr() if self.use_native_v else None, self.vaff.data_ptr() if self.use_native_v else None,
             self.v_outliers.data_ptr() if sp else None, self.v_outlier_idx.data_ptr() if sp else None,
             self.n_out, self.H, self.Lmax, L, rope.data_ptr(), npos, float(rope_theta), self.n_sink,
             self.sink_k.data_ptr() if ns else None, self.sink_v.data_ptr() if ns else None, ns,

@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) append_kv_fused_kernel(
     const float* __restrict__ klut_sub, const float* __restrict__ k_thr_lo, const float* __restrict__ k_thr_hi,
     float* __restrict__ k_out, int32_t* __restrict__ k_idx,
     const float* __restrict__ v_new, uint32_t* __restrict__ vcache, const float* __restrict__ v_cent,
-    float* __restrict__ vlut_tok, float* __restrict__ v_aff, float* __restrict__ v_out, int32_t* __restrict__ v_idx) {
+    const float* __restrict__ v_cent_deq, float* __restrict__ vlut_tok, float* __restrict__ v_aff, float* __restrict__ v_out, int32_t* __restrict__ v_idx) {
   constexpr int N = Layout<BITS>::kLevels;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_x = reinterpret_cast<float*>(smem_raw);                 // [hidden] raw values
@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) append_kv_fused_kernel(
   __shared__ uint32_t s_cnt[2];
   __shared__ float s_vlut[16];
   __shared__ float s_thr[2];
+  __shared__ float s_vzp;   // value the zero-point code dequantises to (Q-Norm: from the shifted centroids)
   const int tid = threadIdx.x;
   const bool isV = blockIdx.x == 1;
   const int n_out = 2 * n_each;
@@ -350,6 +351,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) append_kv_fused_kernel(
       const float e = __fadd_rn(__fmul_rn(v_cent[tid], sf), off);  // two roundings, as torch mul then add
       s_vlut[tid] = e;
       vlut_tok[slot * N + tid] = e;
+      if (tid == Layout<BITS>::kZeroPoint)   // modeling_llama.py:1126,1149-1152
+        s_vzp = (v_cent_deq != nullptr) ? __fadd_rn(__fmul_rn(v_cent_deq[tid], sf), off) : e;
       if (tid == 0 && v_aff != nullptr) { v_aff[2 * slot] = sf; v_aff[2 * slot + 1] = off; }
     }
     // outliers are the elements strictly beyond the thresholds (the n_each larger / smaller ones)
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) append_kv_fused_kernel(
       const int local = upper ? tid : tid - n_each;
       if ((uint32_t)local < have) {
         const int j = s_sel_idx[tid];
-        s_sel_val[tid] = s_x[j] - s_vlut[Layout<BITS>::kZeroPoint];  // modeling_llama.py:1169
+        s_sel_val[tid] = s_x[j] - s_vzp;  // modeling_llama.py:1169
       } else {  // exact ties at the threshold: fewer than n_each strict outliers -> pad (value 0, index 0)
         s_sel_idx[tid] = 0;
         s_sel_val[tid] = 0.f;
@@ -488,8 +491,8 @@ static int append_parallel(int bits, bool isv, int32_t* cache, const float* lut,
 template <int BITS>
 static int launch_fused(int hidden, int64_t Lmax, int64_t slot, int n_each, const float* k_new, uint32_t* kcache,
                         const float* klut, const float* klut_sub, const float* ktl, const float* kth, float* kout,
-                        int32_t* kidx, const float* v_new, uint32_t* vcache, const float* vcent, float* vlut,
-                        float* vaff, float* vout, int32_t* vidx, cudaStream_t st) {
+                        int32_t* kidx, const float* v_new, uint32_t* vcache, const float* vcent, const float* vcent_deq,
+                        float* vlut, float* vaff, float* vout, int32_t* vidx, cudaStream_t st) {
   const size_t smem = (size_t)hidden * (4 + 4 + 1);
   static bool attr_done[5] = {false, false, false, false, false};
   if (!attr_done[BITS]) {
@@ -499,7 +502,7 @@ static int launch_fused(int hidden, int64_t Lmax, int64_t slot, int n_each, cons
   }
   append_kv_fused_kernel<BITS><<<2, kFusedThreads, smem, st>>>(hidden, Lmax, slot, n_each, k_new, kcache, klut,
                                                               klut_sub, ktl, kth, kout, kidx, v_new, vcache, vcent,
-                                                              vlut, vaff, vout, vidx);
+                                                              vcent_deq, vlut, vaff, vout, vidx);
   KVQ_LAUNCH_CHECK();
   return 0;
 }
@@ -542,8 +545,8 @@ int kvq_append_v_sparse_parallel(int bits, int32_t* cache, const float* lut_tok,
 int kvq_append_kv_fused(int bits, int H, int64_t Lmax, int64_t slot, int n_each, const float* k_new,
                         int32_t* kcache, const float* klut, const float* klut_sub, const float* k_thr_lower,
                         const float* k_thr_upper, float* k_outliers, int32_t* k_outlier_idx, const float* v_new,
-                        int32_t* vcache, const float* v_cent, float* vlut_tok, float* v_aff, float* v_outliers,
-                        int32_t* v_outlier_idx, void* stream) {
+                        int32_t* vcache, const float* v_cent, const float* v_cent_deq, float* vlut_tok, float* v_aff,
+                        float* v_outliers, int32_t* v_outlier_idx, void* stream) {
   if (!k_new || !kcache || !klut || !klut_sub || !k_thr_lower || !k_thr_upper || !k_outliers || !k_outlier_idx ||
       !v_new || !vcache || !v_cent || !vlut_tok || !v_outliers || !v_outlier_idx)
     return KVQ_E_NULL;
@@ -555,9 +558,9 @@ int kvq_append_kv_fused(int bits, int H, int64_t Lmax, int64_t slot, int n_each,
   uint32_t* kc = reinterpret_cast<uint32_t*>(kcache);
   uint32_t* vc = reinterpret_cast<uint32_t*>(vcache);
   switch (bits) {
-    case 4: return launch_fused<4>(hidden, Lmax, slot, n_each, k_new, kc, klut, klut_sub, k_thr_lower, k_thr_upper, k_outliers, k_outlier_idx, v_new, vc, v_cent, vlut_tok, v_aff, v_outliers, v_outlier_idx, st);
-    case 3: return launch_fused<3>(hidden, Lmax, slot, n_each, k_new, kc, klut, klut_sub, k_thr_lower, k_thr_upper, k_outliers, k_outlier_idx, v_new, vc, v_cent, vlut_tok, v_aff, v_outliers, v_outlier_idx, st);
-    case 2: return launch_fused<2>(hidden, Lmax, slot, n_each, k_new, kc, klut, klut_sub, k_thr_lower, k_thr_upper, k_outliers, k_outlier_idx, v_new, vc, v_cent, vlut_tok, v_aff, v_outliers, v_outlier_idx, st);
+    case 4: return launch_fused<4>(hidden, Lmax, slot, n_each, k_new, kc, klut, klut_sub, k_thr_lower, k_thr_upper, k_outliers, k_outlier_idx, v_new, vc, v_cent, v_cent_deq, vlut_tok, v_aff, v_outliers, v_outlier_idx, st);
+    case 3: return launch_fused<3>(hidden, Lmax, slot, n_each, k_new, kc, klut, klut_sub, k_thr_lower, k_thr_upper, k_outliers, k_outlier_idx, v_new, vc, v_cent, v_cent_deq, vlut_tok, v_aff, v_outliers, v_outlier_idx, st);
+    case 2: return launch_fused<2>(hidden, Lmax, slot, n_each, k_new, kc, klut, klut_sub, k_thr_lower, k_thr_upper, k_outliers, k_outlier_idx, v_new, vc, v_cent, v_cent_deq, vlut_tok, v_aff, v_outliers, v_outlier_idx, st);
     default: return KVQ_E_BITS;
   }
 }

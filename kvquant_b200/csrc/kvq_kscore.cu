@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const
 #pragma unroll
     for (int i = 0; i < NRW; ++i) wq[d][i] = 0;
   auto fetch = [&](uint32_t* dst, const unsigned char* base, bool ok, int a, int hl) {
-    if (ok) {
+    if (ok && (FULL || hl < nh)) {   // heads past nh do not exist in the cache: never touch them
 #pragma unroll
       for (int i = 0; i < NRW; ++i)
         dst[i] = ld_stream_u32(reinterpret_cast<const uint32_t*>(

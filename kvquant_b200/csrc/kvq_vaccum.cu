@@ -558,10 +558,12 @@ int kvq_attend(int bits, const float* q, const int32_t* kcache, const float* klu
     rc = k_scores_fused(bits, q, kcache, scores, stride, klut, k_outliers, k_outlier_idx, n_out, H, Lmax, L,
                         rope_cos_sin, rope_npos, theta, pos_offset, gmax, scale, st);
     if (rc) return rc;
-    if (native_v) {
+    rc = KVQ_E_UNSUPPORTED;
+    if (native_v)
       rc = v_native_dispatch(bits, scores, stride, gmax, vcache, v_cent, v_aff, v_outliers, v_outlier_idx, n_out, H,
                              Lmax, L, part_o, part_l, &n_cta, st);
-    } else {
+    // shapes whose native tile does not fit shared memory (e.g. 13B at 4 bits) fall back to the per-token-LUT kernel
+    if (rc == KVQ_E_UNSUPPORTED && vlut_tok != nullptr) {
       VParams p{};
       p.score = scores; p.lut_tok = vlut_tok; p.out = part_o; p.out_l = part_l; p.gmax = gmax;
       p.outliers = v_outliers; p.outlier_idx = v_outlier_idx;

@@ -456,7 +456,10 @@ class OracleCache:
     """QuantK + QuantV state for one layer, filled token by token exactly as
     QuantK/QuantV.forward_fused_sparse do (ML.py:653-751, 1069-1176)."""
 
-    def __init__(self, bits, num_heads, max_len, klut, v_cent, include_sparse=True, sparsity_threshold=0.99):
+    def __init__(self, bits, num_heads, max_len, klut, v_cent, include_sparse=True, sparsity_threshold=0.99,
+                 v_norm=None):
+        """v_norm = (normscale, normoffset) enables Q-Norm on V (ML.py:1054-1066,1115-1118); K Q-Norm is enabled by
+        klut['lut2'] (ML.py:485-488): packing uses LUT, dequantisation and outlier subtraction use LUT2."""
         self.bits = bits
         self.H = num_heads
         self.hidden = num_heads * HEAD_DIM
@@ -469,6 +472,9 @@ class OracleCache:
         self.kwords = np.zeros((W, max_len), dtype=np.int32)
         self.vwords = np.zeros((W, max_len), dtype=np.int32)
         self.vlut = np.zeros((max_len, 2 ** bits), dtype=np.float32)
+        self.v_norm = v_norm
+        self.v_cent2 = None if v_norm is None else ((self.v_cent * F32(v_norm[0])).astype(np.float32) + F32(v_norm[1])).astype(np.float32)
+        self.vlut2 = np.zeros((max_len, 2 ** bits), dtype=np.float32) if v_norm is not None else None
         n_out = 2 * self.n_each
         self.k_out = np.zeros((max_len, n_out), dtype=np.float32)
         self.k_idx = np.zeros((max_len, n_out), dtype=np.int32)
@@ -487,7 +493,11 @@ class OracleCache:
             hi, lo, ui, li = v_thresholds(v, self.n_each)
             self.vlut[t] = v_token_lut(self.v_cent, hi, lo)
             codes = append_v_codes(v, self.vlut[t], self.bits, lo, hi)
-            self.v_out[t], self.v_idx[t] = v_outlier_row(v, ui, li, self.vlut[t][zero_point_code(self.bits)])
+            zrow = self.vlut[t]
+            if self.v_norm is not None:   # ML.py:1115-1118, 1149-1152: zero-point taken from the Q-Norm table
+                self.vlut2[t] = v_token_lut(self.v_cent2, hi, lo)
+                zrow = self.vlut2[t]
+            self.v_out[t], self.v_idx[t] = v_outlier_row(v, ui, li, zrow[zero_point_code(self.bits)])
         else:
             v = np.asarray(v, dtype=np.float32)
             self.vlut[t] = v_token_lut(self.v_cent, v.max(), v.min())  # compute_lut (ML.py:318-349)
@@ -496,13 +506,14 @@ class OracleCache:
         self.len += 1
 
     def k_scores(self, q, rope_theta=10000.0, pos_offset=0):
-        s = k_scores_dense(q, self.kwords, self.klut["lut"], self.bits, self.len, rope_theta, pos_offset, self.H)
+        deq = self.klut["lut2"] if self.klut.get("lut2") is not None else self.klut["lut"]
+        s = k_scores_dense(q, self.kwords, deq, self.bits, self.len, rope_theta, pos_offset, self.H)
         if self.sparse:
             s = s + k_scores_outliers(q, self.k_out, self.k_idx, self.len, rope_theta, pos_offset, self.H)
         return s
 
     def v_output(self, p):
-        o = v_out_dense(p, self.vwords, self.vlut, self.bits, self.len, self.H)
+        o = v_out_dense(p, self.vwords, self.vlut2 if self.v_norm is not None else self.vlut, self.bits, self.len, self.H)
         if self.sparse:
             o = o + v_out_outliers(p, self.v_out, self.v_idx, self.len, self.H)
         return o

@@ -260,3 +260,65 @@ def test_fused_attend_within_1e3_of_oracle_chain(bits, L, sparse, n_sink):
         p16, o16 = O.attend_reference(s, v_fn, 32)
         e_max, e_l2 = rel_err(out, o16.astype(np.float64))
         assert e_max < 2e-3 and e_l2 < 1e-3, (e_max, e_l2)  # 2e-3: two fp16 ulps of the reference's own rounding
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# other model shapes / options
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bits", [4, 3])
+def test_llama13b_shape_fused_append_and_attend(bits):
+    """H = 40 (hidden 5120, 52 outlier columns): partial head groups in the K kernel, two units per thread in V,
+    and (4-bit) the native V tile does not fit shared memory -> per-token-LUT kernel fallback."""
+    from kvquant_b200.cache import LayerCache
+    H, L = 40, 150
+    klut, vcent = quantizer(bits, H=H)
+    c, k, v = oracle_cache(bits, L, H=H)
+    assert c.k_out.shape[1] == 52
+    lc = LayerCache.from_luts(bits, H, c.Lmax, klut, vcent, device=DEV)
+    for t in range(L):
+        lc.append(cu(k[t]), cu(v[t]))
+    assert np.array_equal(lc.kcache.cpu().numpy().reshape(-1, c.Lmax), c.kwords)
+    assert np.array_equal(lc.vcache.cpu().numpy().reshape(-1, c.Lmax), c.vwords)
+    assert np.array_equal(lc.k_outlier_idx.cpu().numpy(), c.k_idx) and np.array_equal(lc.v_outlier_idx.cpu().numpy(), c.v_idx)
+    assert np.array_equal(lc.k_outliers.cpu().numpy(), c.k_out) and np.array_equal(lc.v_outliers.cpu().numpy(), c.v_out)
+    q = O.rope_rotate_q(spec(H).q_vec(4), L, 10000.0)
+    _, want = O.attend_ideal(c.k_scores(q), c.v_output)
+    out = lc.attend(cu(q)).cpu().numpy()
+    assert rel_err(out, want)[0] < 1e-3
+
+
+def test_qnorm_2bit_native_path():
+    """Q-Norm (reference 2-bit path, modeling_llama.py:485-488, 1115-1118): codes against LUT, dequantisation and
+    outlier residuals against LUT2 = (cent*normscale+normoffset)*range+zp."""
+    from kvquant_b200.cache import LayerCache
+    from _util import synth
+    bits, L, H = 2, 200, 32
+    sp = spec()
+    cal = synth.calibrate(sp, bits, calib_tokens=512, seed=7)
+    ns, no = 1.0625, -0.015625
+    klut = O.build_k_lut(cal["k"][0], cal["k"][1], cal["k"][2][0], normscale=ns, normoffset=no)
+    vcent = np.sort(cal["v"][2][0].ravel().astype(np.float32))
+    c = O.OracleCache(bits, H, 320, klut, vcent, v_norm=(ns, no))
+    k, v = sp.k_tokens(L, 61), sp.v_tokens(L, 62)
+    lc = LayerCache.from_luts(bits, H, 320, klut, vcent, device=DEV, v_norm=(ns, no))
+    for t in range(L):
+        c.append(k[t], v[t])
+        lc.append(cu(k[t]), cu(v[t]))
+    assert np.array_equal(lc.kcache.cpu().numpy().reshape(-1, 320), c.kwords)
+    assert np.array_equal(lc.k_outliers.cpu().numpy(), c.k_out) and np.array_equal(lc.v_outliers.cpu().numpy(), c.v_out)
+    q = O.rope_rotate_q(sp.q_vec(8), L, 10000.0)
+    _, want = O.attend_ideal(c.k_scores(q), c.v_output)
+    assert rel_err(lc.attend(cu(q)).cpu().numpy(), want)[0] < 1e-3
+
+
+def test_error_codes_are_loud():
+    from kvquant_b200 import _lib
+    lib = _lib.load()
+    z = torch.zeros(16, device=DEV)
+    assert lib.kvq_append_k(5, z.data_ptr(), z.data_ptr(), z.data_ptr(), 32, 64, 0, None) == -1       # bits
+    assert lib.kvq_append_k(4, z.data_ptr(), z.data_ptr(), z.data_ptr(), 32, 64, 64, None) == -2      # slot >= Lmax
+    assert lib.kvq_append_k(4, None, z.data_ptr(), z.data_ptr(), 32, 64, 0, None) == -3               # NULL
+    with pytest.raises(_lib.KVQuantError):
+        _lib.check(-4, "x")
+    # V / attend need Lmax % 4 == 0 (TMA row pitch)
+    assert lib.kvq_v_matvec(4, z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 1, 32, 66, 8, None, None, 0, None) == -4
