@@ -42,7 +42,7 @@ template <int BITS> struct VNCfg {
   static constexpr int W = Layout<BITS>::kWords;
   static constexpr int IDXBITS = (BITS == 4) ? 8 : (BITS == 3 ? 6 : 4);  // two codes
   static constexpr int TABN = 1 << IDXBITS;                               // entries per lane
-  static constexpr int NP = (BITS == 3) ? 16 : 4;                         // float2 accumulators per unit
+  static constexpr int NP = (BITS == 3) ? 6 : 4;                          // float2 accumulators per unit
 };
 
 struct VNSmem { uint32_t stage_bytes, off_tab, off_w, off_ws, off_oacc, off_bar, total; };
@@ -69,29 +69,20 @@ __device__ __forceinline__ void ffma2v(float2& acc, const float2 a, const float2
       : "+f"(acc.x), "+f"(acc.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
 }
 
-// One unit over tokens [4*q0, 4*(q0+nq)) of the tile.  4/2-bit: unit = packed word row (8 channels = 4 pair
-// lookups per token), all 32 tokens.  3-bit: unit = a whole 32-channel group (3 consecutive word rows, 16 pair
-// lookups per token; 6-bit fields that straddle a word come out of a funnel shift) for ONE QUARTER of the tile's
-// tokens -- 4 threads per group keep all 512 threads busy with a single code path.
-// row_off/swz: the unit's (first) word row in the 128B-swizzled stage; tab = shared address of the lane's table
-// column (table base + lane*8); wsrow -> ws[head][0..31].
-template <int BITS>
-__device__ __forceinline__ void vn_tile_unit(const unsigned char* stage, const uint32_t* row_off, const uint32_t* swz,
-                                             int part, uint32_t tab, const float* __restrict__ wsrow,
-                                             float2* __restrict__ acc, const int q0) {
-  constexpr int NQ = (BITS == 3) ? 2 : 8;
+// 32 tokens of one unit.  row_off/swz: this unit's word row in the 128B-swizzled stage; tab = shared address of the
+// lane's table column (table base + lane*8); wsrow -> ws[head][0..31].
+template <int BITS, int SUB>
+__device__ __forceinline__ void vn_tile_unit(const unsigned char* stage, uint32_t row_off, uint32_t swz,
+                                             uint32_t row_off2, uint32_t swz2, int part, uint32_t tab,
+                                             const float* __restrict__ wsrow, float2* __restrict__ acc) {
 #pragma unroll 2
-  for (int q = q0; q < q0 + NQ; ++q) {
-    const uint4 wa = *reinterpret_cast<const uint4*>(stage + row_off[0] + ((q ^ swz[0]) << 4));
-    uint4 wb = make_uint4(0, 0, 0, 0), wc = make_uint4(0, 0, 0, 0);
-    if constexpr (BITS == 3) {
-      wb = *reinterpret_cast<const uint4*>(stage + row_off[1] + ((q ^ swz[1]) << 4));
-      wc = *reinterpret_cast<const uint4*>(stage + row_off[2] + ((q ^ swz[2]) << 4));
-    }
+  for (int q = 0; q < 8; ++q) {
+    const uint4 wa = *reinterpret_cast<const uint4*>(stage + row_off + ((q ^ swz) << 4));
+    uint4 wb = make_uint4(0, 0, 0, 0);
+    if constexpr (BITS == 3 && SUB < 2) wb = *reinterpret_cast<const uint4*>(stage + row_off2 + ((q ^ swz2) << 4));
     const float4 ws4 = *reinterpret_cast<const float4*>(wsrow + 4 * q);
     const uint32_t wav[4] = {wa.x, wa.y, wa.z, wa.w};
     const uint32_t wbv[4] = {wb.x, wb.y, wb.z, wb.w};
-    const uint32_t wcv[4] = {wc.x, wc.y, wc.z, wc.w};
     const float wsv[4] = {ws4.x, ws4.y, ws4.z, ws4.w};
 #pragma unroll
     for (int tt = 0; tt < 4; ++tt) {
@@ -107,17 +98,16 @@ __device__ __forceinline__ void vn_tile_unit(const unsigned char* stage, const u
         for (int b = 0; b < 4; ++b)  // nibble b of this thread's half word
           ffma2v(acc[b], ws2, lds_f2_dyn((b < 2 ? ((w << (8 - 4 * b)) & 0xF00u) : ((w >> (4 * b - 8)) & 0xF00u)) + tab));
       } else {
-        const uint32_t w0 = wav[tt], w1 = wbv[tt], w2 = wcv[tt];
+        const uint32_t w = wav[tt];
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {   // pair m = channels 2m, 2m+1 = 6 bits at bit 6m of the 96-bit group
-          const int bit = 6 * m;
-          uint32_t x;                    // field moved to bits 8..13
-          if (bit + 6 <= 32) x = (bit >= 8) ? (w0 >> (bit - 8)) : (w0 << (8 - bit));
-          else if (bit < 32) x = __funnelshift_r(w0, w1, bit - 8);            // m = 5: bits 30..35
-          else if (bit + 6 <= 64) x = (bit - 32 >= 8) ? (w1 >> (bit - 40)) : (w1 << (40 - bit));
-          else if (bit < 64) x = __funnelshift_r(w1, w2, bit - 40);           // m = 10: bits 60..65
-          else x = (bit - 64 >= 8) ? (w2 >> (bit - 72)) : (w2 << (72 - bit));
-          ffma2v(acc[m], ws2, lds_f2_dyn((x & 0x3F00u) + tab));
+        for (int b = 0; b < 5; ++b) {  // 6-bit fields at bit SUB + 6b
+          const int s = SUB + 6 * b;
+          const uint32_t x = (s >= 8) ? (w >> (s - 8)) : (w << (8 - s));
+          ffma2v(acc[b], ws2, lds_f2_dyn((x & 0x3F00u) + tab));
+        }
+        if constexpr (SUB < 2) {  // the straddling code (loc 10 / 21); high half of the index is 0 -> .y is unused
+          const uint32_t c = ((w >> (30 + SUB)) | (wbv[tt] << (2 - SUB))) & 0x7u;
+          ffma2v(acc[5], ws2, lds_f2_dyn((c << 8) + tab));
         }
       }
     }
@@ -149,22 +139,22 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
   }
   const uint32_t tab = smem_u32(s_tab) + lane * 8;
 
-  // ---- thread -> unit mapping (up to 2 units per thread) ---------------------------------------------------------
-  // 4-bit: unit = word row; 2-bit: half a word row; 3-bit: (32-channel group, token quarter)
-  int u_row[2], u_head[2], u_ch0[2], u_part[2], u_q0[2];
+  // ---- thread -> unit mapping (same as kvq_vaccum.cu) ------------------------------------------------------------
+  int u_row[2], u_head[2], u_ch0[2], u_part[2];
   bool u_on[2];
+  int sub = 0;
   if constexpr (BITS == 3) {
+    sub = warp % 3;
+    const int tri = warp / 3;
     const int ngroups = p.H * 4;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const int uu = tid + i * kNThreads;
-      const int quarter = uu / ngroups, gi = uu - quarter * ngroups;
-      u_on[i] = uu < 4 * ngroups;
-      u_row[i] = 3 * gi;
+      const int gi = tri * 32 + lane + i * 160;
+      u_on[i] = (warp < 15) && gi < ngroups;
+      u_row[i] = 3 * gi + sub;
       u_head[i] = gi >> 2;
-      u_ch0[i] = (gi & 3) * 32;
+      u_ch0[i] = (gi & 3) * 32 + (sub == 0 ? 0 : (sub == 1 ? 11 : 22));
       u_part[i] = 0;
-      u_q0[i] = 2 * quarter;
     }
   } else {
     const int nunits = p.H * 16;
@@ -172,23 +162,22 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
     for (int i = 0; i < 2; ++i) {
       const int u = tid + i * kNThreads;
       u_on[i] = u < nunits;
-      u_q0[i] = 0;
       if constexpr (BITS == 4) { u_row[i] = u; u_part[i] = 0; u_head[i] = u >> 4; u_ch0[i] = (u & 15) * 8; }
       else { u_row[i] = u >> 1; u_part[i] = u & 1; u_head[i] = u >> 4; u_ch0[i] = ((u >> 1) & 7) * 16 + (u & 1) * 8; }
     }
   }
   // 128B swizzle: 16-byte chunk index ^= row & 7; TMA boxes are [32 tokens x box_rows rows] (box_rows % 8 == 0), laid
   // out back to back, so row r simply sits at r*128 inside the stage
-  uint32_t r_off[2][3], r_swz[2][3];
+  uint32_t r_off[2], r_swz[2], r_off2[2], r_swz2[2];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int w = 0; w < 3; ++w) {
-      int r = (u_on[i] ? u_row[i] : 0) + w;
-      if (r >= rows) r = rows - 1;
-      r_off[i][w] = (uint32_t)r * 128u;
-      r_swz[i][w] = (uint32_t)(r & 7);
-    }
+  for (int i = 0; i < 2; ++i) {
+    const int r = u_on[i] ? u_row[i] : 0;
+    r_off[i] = (uint32_t)r * 128u;
+    r_swz[i] = (uint32_t)(r & 7);
+    const int r2 = (r + 1 < rows) ? r + 1 : r;
+    r_off2[i] = (uint32_t)r2 * 128u;
+    r_swz2[i] = (uint32_t)(r2 & 7);
+  }
   float2 acc[2][NP];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -300,7 +289,13 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
     for (int i = 0; i < 2; ++i) {
       if (u_on[i]) {
         const float* wsrow = wsbuf + u_head[i] * kNT;
-        vn_tile_unit<BITS>(stage, r_off[i], r_swz[i], u_part[i], tab, wsrow, acc[i], u_q0[i]);
+        if constexpr (BITS == 3) {
+          if (sub == 0) vn_tile_unit<3, 0>(stage, r_off[i], r_swz[i], r_off2[i], r_swz2[i], 0, tab, wsrow, acc[i]);
+          else if (sub == 1) vn_tile_unit<3, 1>(stage, r_off[i], r_swz[i], r_off2[i], r_swz2[i], 0, tab, wsrow, acc[i]);
+          else vn_tile_unit<3, 2>(stage, r_off[i], r_swz[i], r_off2[i], r_swz2[i], 0, tab, wsrow, acc[i]);
+        } else {
+          vn_tile_unit<BITS, 0>(stage, r_off[i], r_swz[i], 0, 0, u_part[i], tab, wsrow, acc[i]);
+        }
       }
     }
     if (has_out) {
@@ -344,20 +339,22 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
   }
   __syncthreads();
   for (int i = tid; i < p.H; i += kNThreads) p.out_l[(int64_t)blockIdx.x * p.H + i] = s_l[i];
-  // units deposit into the shared accumulator (3-bit: four token-quarters per channel; also holds the outliers)
+  float* obase = p.out_o + (int64_t)blockIdx.x * hidden;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     if (u_on[i]) {
+      const float hoff = s_off[u_head[i]];
+      const int nch = (BITS == 3) ? (sub == 2 ? 10 : 11) : 8;
 #pragma unroll
       for (int k = 0; k < 2 * NP; ++k) {
-        const int j = u_head[i] * kHeadDim + u_ch0[i] + k;
-        atomicAdd(&s_oacc[j], (k & 1) ? acc[i][k >> 1].y : acc[i][k >> 1].x);
+        if (k < nch) {
+          const int j = u_head[i] * kHeadDim + u_ch0[i] + k;
+          const float v = (k & 1) ? acc[i][k >> 1].y : acc[i][k >> 1].x;
+          obase[j] = v + hoff + s_oacc[j];
+        }
       }
     }
   }
-  __syncthreads();
-  float* obase = p.out_o + (int64_t)blockIdx.x * hidden;
-  for (int j = tid; j < hidden; j += kNThreads) obase[j] = s_oacc[j] + s_off[j >> 7];
 }
 
 constexpr uint32_t kVNSmemBudget = 227u * 1024u;
