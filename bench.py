@@ -149,6 +149,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallelism", default="pp", choices=["pp", "sp"],
+                    help="N>1: pp = layer-group pipeline (the reference's scheme, north_star); sp = sequence-sharded "
+                         "attention with replicated weights (SURVEY 8e-2 / 8f-1)")
     ap.add_argument("--torch-profile", default="", help="write a per-kernel table of 3 graph replays to this file (diagnostic)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -176,10 +179,14 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = kd.DecodeConfig.llama7b(bits=bits, n_sink=n_sink, max_len=L + 64)
+    sp_mode = (args.parallelism == "sp" and world > 1)
+    if sp_mode and L % world:
+        raise SystemExit("sp needs seq_len divisible by the number of GPUs")
+    L_local = L // world if sp_mode else L
+    cfg = kd.DecodeConfig.llama7b(bits=bits, n_sink=n_sink, max_len=L_local + 64)
     sp, quantizer = build_quantizer(bits, cfg.n_heads, dev)
     config = {"workload": args.workload, "description": desc, "bits": bits, "seq_len": L + n_sink, "n_sink": n_sink,
-              "outliers": "1% (21+21 per token per cache)", "layers": cfg.n_layers, "parallelism": "pp%d" % world,
+              "outliers": "1% (21+21 per token per cache)", "layers": cfg.n_layers, "parallelism": ("sp%d" if sp_mode else "pp%d") % world,
               "l2_policy": "inputs larger than L2: every step streams all layers' caches (>= 4 GB) and 13.5 GB of weights",
               "step": "one CUDA-graph replay of a full decode step at fixed cache length"}
 
@@ -209,17 +216,24 @@ def main():
         return 0
 
     # ---------------------------------------------------------------------------------------------------------
-    lo, hi = kd.partition_layers(cfg.n_layers, world, rank)
-    stage = kd.DecoderStage(cfg, lo, hi, dev, quantizer, seed=0, with_head=(rank == 0))
+    if sp_mode:
+        lo, hi = 0, cfg.n_layers
+        stage = kd.DecoderStage(cfg, lo, hi, dev, quantizer, seed=0, with_head=True, sp=(rank, world))
+        stage.global_pos = n_sink + L
+    else:
+        lo, hi = kd.partition_layers(cfg.n_layers, world, rank)
+        stage = kd.DecoderStage(cfg, lo, hi, dev, quantizer, seed=0, with_head=(rank == 0))
     t_fill = time.time()
     for i, ly in enumerate(stage.layers):
-        synth.fill_layer_cache_gpu(ly.cache, sp, L, seed=lo + i)
+        if sp_mode:
+            ly.cache.pos_base = rank * L_local
+        synth.fill_layer_cache_gpu(ly.cache, sp, L_local, seed=(lo + i) * 16 + (rank if sp_mode else 0))
     torch.cuda.synchronize()
     t_fill = time.time() - t_fill
 
     n0 = _lib.launch_count()
-    gs = kd.GraphedStage(stage, L, first=(rank == 0), last_to_logits=(world == 1))
-    launches_per_step = (_lib.launch_count() - n0) // 3   # 2 eager warm-up passes + 1 capture pass
+    gs = kd.GraphedStage(stage, L_local, first=(rank == 0 or sp_mode), last_to_logits=(world == 1 or sp_mode))
+    launches_per_step = (_lib.launch_count() - n0) // (5 if sp_mode else 3)   # eager warm-up passes + 1 capture pass
     if world > 1 and rank == 0:
         head_graph_in = torch.zeros(cfg.hidden, dtype=torch.float16, device=dev)
     pinned_tok = torch.zeros(1, dtype=torch.long).pin_memory()
@@ -228,7 +242,7 @@ def main():
 
     def step_device():
         """one decode step, inputs resident on the device"""
-        if world == 1:
+        if world == 1 or sp_mode:
             gs.replay()
             logits_dev[0] = gs.logits
             return
@@ -242,11 +256,11 @@ def main():
 
     def step_e2e(i):
         """same step through host buffers: token id H2D from pinned memory, logits D2H to pinned memory"""
-        if rank == 0:
+        if rank == 0 or sp_mode:
             pinned_tok[0] = (17 * i + 3) % cfg.vocab
             gs.tok.copy_(pinned_tok, non_blocking=True)
         step_device()
-        if rank == 0:
+        if rank == 0 or sp_mode:
             pinned_logits.copy_(logits_dev[0], non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
@@ -313,7 +327,7 @@ def main():
             torch.cuda.synchronize()
             return a.elapsed_time(b) / (reps * len(layers))
 
-        Lq = L + 1
+        Lq = L_local + (0 if (sp_mode and rank != world - 1) else 1)
         ms_att = time_loop(lambda ly: ly.cache.attend(q, rope_theta=cfg.rope_theta))
         from kvquant_b200 import quant_cuda as qc
         mulK = torch.zeros((1, cfg.n_heads, Lq), device=dev)
@@ -336,14 +350,15 @@ def main():
                 "algorithmic_bytes_per_launch": b_att, "ms_per_launch": ms_att,
                 "per_kernel": {"k_scores_kernel": {"ms": ms_k, "bytes": b_k, "gbs": b_k / ms_k / 1e6, "frac": b_k / ms_k / 1e6 / peak},
                                "v_accum_kernel": {"ms": ms_v, "bytes": b_v, "gbs": b_v / ms_v / 1e6, "frac": b_v / ms_v / 1e6 / peak}},
-                "attend_share_of_step": ms_att * cfg.n_layers / world / ms_step}
+                "attend_share_of_step": ms_att * len(layers) / ms_step}
         if not args.no_cpu_baseline:
             lc = layers[0].cache
             arrs = dict(kcache=lc.kcache.cpu().numpy(), vcache=lc.vcache.cpu().numpy(), klut=lc.klut.cpu().numpy(),
                         vlut=lc.vlut.cpu().numpy(), k_out=lc.k_outliers.cpu().numpy(), k_idx=lc.k_outlier_idx.cpu().numpy(),
                         v_out=lc.v_outliers.cpu().numpy(), v_idx=lc.v_outlier_idx.cpu().numpy(), q=q.cpu().numpy())
-            tok_s, cores, sample = cpu_baseline_run(arrs, bits, cfg.n_heads, cfg.max_len, L, n_out, cfg.n_layers,
-                                                    cfg.rope_theta, n_sink, budget_s=15.0)
+            tok_s, cores, sample = cpu_baseline_run(arrs, bits, cfg.n_heads, cfg.max_len, L_local, n_out,
+                                                    cfg.n_layers * (world if sp_mode else 1), cfg.rope_theta, n_sink,
+                                                    budget_s=15.0)
             cpu_b = {"value": tok_s, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:

@@ -118,7 +118,7 @@ KVQ_API int kvq_v_matvec(int bits, const float* score, const int32_t* cache, flo
  * LUT_t[i] = v_cent[i]*sf_t + off_t (what kvq_append_kv_fused writes); when both are given the affine form is used.
  * scratch: device buffer of kvq_attend_scratch_bytes(H, L) bytes.
  * sink_k: f16 [H,128,n_sink] post-RoPE keys, sink_v: f16 [H,n_sink,128] (modeling_llama.py:1464-1466), or NULL.
- * out: f32 [H,128].
+ * out: f32 [H,128].  out_lse (optional): f32 [H], log-sum-exp of the scaled scores over this call's tokens.
  * ------------------------------------------------------------------------------------------------------------- */
 KVQ_API int64_t kvq_attend_scratch_bytes(int H, int64_t L);
 KVQ_API int kvq_attend(int bits, const float* q,
@@ -129,7 +129,10 @@ KVQ_API int kvq_attend(int bits, const float* q,
                int n_out, int H, int64_t Lmax, int64_t L,
                const float* rope_cos_sin, int64_t rope_npos, float theta, int pos_offset,
                const void* sink_k, const void* sink_v, int n_sink,
-               float* out, void* scratch, void* stream);
+               float* out, float* out_lse, void* scratch, void* stream);
+/* Merge of n_parts partial results of kvq_attend over disjoint token ranges (sequence-sharded decode):
+ * parts f32 [n_parts, H*128 + H] = (out[H,128], lse[H]) per part, as produced with out_lse != NULL; out f32 [H,128]. */
+KVQ_API int kvq_attend_merge(const float* parts, int n_parts, int H, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Fused device-side append (native op): replaces the whole host round trip of

@@ -32,7 +32,8 @@ SIGNATURES = {
     "kvq_v_matvec": (_c_int, [_c_int, _p, _p, _p, _p, _c_int, _c_int, _c_i64, _c_i64, _p, _p, _c_int, _p]),
     "kvq_attend_scratch_bytes": (_c_i64, [_c_int, _c_i64]),
     "kvq_attend": (_c_int, [_c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_i64, _c_i64, _p,
-                            _c_i64, _c_f, _c_int, _p, _p, _c_int, _p, _p, _p]),
+                            _c_i64, _c_f, _c_int, _p, _p, _c_int, _p, _p, _p, _p]),
+    "kvq_attend_merge": (_c_int, [_p, _c_int, _c_int, _p, _p]),
     "kvq_append_kv_fused": (_c_int, [_c_int, _c_int, _c_i64, _c_i64, _c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                      _p, _p, _p, _p, _p, _p, _p]),
     "kvq_k_spmv_csr": (_c_int, [_p, _p, _p, _p, _p, _p, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_f, _c_int, _p]),

@@ -85,6 +85,7 @@ class LayerCache:
         self.v_outlier_idx = torch.zeros((self.Lmax, self.n_out), dtype=torch.int32, device=dev)
         self.len = 0          # tokens in the quantised cache
         self.n_sink = int(n_sink)
+        self.pos_base = 0     # absolute position of slot 0 minus n_sink (non-zero for a sequence shard)
         self.sink_k = self.sink_v = None
         self._scratch = None
         self._out = torch.empty((self.H, HEAD_DIM), dtype=torch.float32, device=dev)
@@ -147,14 +148,16 @@ class LayerCache:
             "kvq_append_kv_fused")
         self.len += 1
 
-    def attend(self, q, rope_theta=10000.0, out=None):
+    def attend(self, q, rope_theta=10000.0, out=None, lse=None):
         """softmax(q.K^T/sqrt(128)).V over sinks + quantised slots.  q: f32 [H,128] already rotated at its own
-        position.  Returns f32 [H,128]."""
+        position.  Returns f32 [H,128].  lse (optional f32 [H]) receives the log-sum-exp of the scaled scores, which
+        lets partial results over disjoint token ranges be merged exactly (sequence-sharded decode)."""
         L = self.len
         need = self.lib.kvq_attend_scratch_bytes(self.H, max(L, 1))
         if self._scratch is None or self._scratch.numel() < need:
             self._scratch = torch.empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=self.device)
-        rope, npos = qc.rope_table(self.device, rope_theta, L + self.n_sink + 1)
+        pos_offset = self.n_sink + self.pos_base
+        rope, npos = qc.rope_table(self.device, rope_theta, L + pos_offset + 1)
         out = self._out if out is None else out
         sp = self.include_sparse
         ns = self.n_sink if self.sink_k is not None else 0
@@ -164,9 +167,10 @@ class LayerCache:
             self.vcache.data_ptr(), self.vlut.data_ptr(),
             self.v_cent_deq.data_ptr() if self.use_native_v else None, self.vaff.data_ptr() if self.use_native_v else None,
             self.v_outliers.data_ptr() if sp else None, self.v_outlier_idx.data_ptr() if sp else None,
-            self.n_out, self.H, self.Lmax, L, rope.data_ptr(), npos, float(rope_theta), self.n_sink,
+            self.n_out, self.H, self.Lmax, L, rope.data_ptr(), npos, float(rope_theta), pos_offset,
             self.sink_k.data_ptr() if ns else None, self.sink_v.data_ptr() if ns else None, ns,
-            out.data_ptr(), self._scratch.data_ptr(), torch.cuda.current_stream().cuda_stream), "kvq_attend")
+            out.data_ptr(), lse.data_ptr() if lse is not None else None, self._scratch.data_ptr(),
+            torch.cuda.current_stream().cuda_stream), "kvq_attend")
         return out
 
     def bytes_per_token(self):

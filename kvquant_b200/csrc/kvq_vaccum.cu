@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(1024) attend_combine_kernel(const float* __res
                                                               int n_part, int H, const float* __restrict__ gmax,
                                                               const float* __restrict__ sink_scores,
                                                               const __half* __restrict__ sink_v, int n_sink,
-                                                              float* __restrict__ out) {
+                                                              float* __restrict__ out, float* __restrict__ out_lse) {
   __shared__ float s_o[8][kHeadDim];
   __shared__ float s_l[8];
   const int h = blockIdx.x, c = threadIdx.x & (kHeadDim - 1), g = threadIdx.x >> 7;
@@ -384,6 +384,23 @@ __global__ void __launch_bounds__(1024) attend_combine_kernel(const float* __res
     const float pi = __expf(sink_scores[h * 64 + i] - m);
     o = fmaf(pi, __half2float(sink_v[((int64_t)h * n_sink + i) * kHeadDim + c]), o);
     l += pi;
+  }
+  out[h * kHeadDim + c] = o / l;
+  if (out_lse != nullptr && c == 0) out_lse[h] = m + __logf(l);   // log-sum-exp of the scaled scores (for cross-GPU merges)
+}
+
+// merge N partial attention results (sequence-sharded decode): parts [N][H*128 + H] = (normalised out[H,128], lse[H])
+__global__ void attend_merge_kernel(const float* __restrict__ parts, int n, int H, float* __restrict__ out) {
+  const int h = blockIdx.x, c = threadIdx.x;   // block = 128
+  const int stride = H * kHeadDim + H;
+  float m = -INFINITY;
+  for (int r = 0; r < n; ++r) m = fmaxf(m, parts[(int64_t)r * stride + H * kHeadDim + h]);
+  float o = 0.f, l = 0.f;
+  for (int r = 0; r < n; ++r) {
+    const float* pr = parts + (int64_t)r * stride;
+    const float w = __expf(pr[H * kHeadDim + h] - m);
+    o = fmaf(w, pr[h * kHeadDim + c], o);
+    l += w;
   }
   out[h * kHeadDim + c] = o / l;
 }
@@ -532,7 +549,7 @@ int kvq_attend(int bits, const float* q, const int32_t* kcache, const float* klu
                const int32_t* k_outlier_idx, const int32_t* vcache, const float* vlut_tok, const float* v_cent,
                const float* v_aff, const float* v_outliers, const int32_t* v_outlier_idx, int n_out, int H, int64_t Lmax, int64_t L, const float* rope_cos_sin,
                int64_t rope_npos, float theta, int pos_offset, const void* sink_k, const void* sink_v, int n_sink,
-               float* out, void* scratch, void* stream) {
+               float* out, float* out_lse, void* scratch, void* stream) {
   if (!q || !kcache || !klut || !vcache || !rope_cos_sin || !out || !scratch) return KVQ_E_NULL;
   const bool native_v = (v_cent != nullptr && v_aff != nullptr);
   if (!native_v && !vlut_tok) return KVQ_E_NULL;
@@ -573,7 +590,15 @@ int kvq_attend(int bits, const float* q, const int32_t* kcache, const float* klu
     if (rc) return rc;
   }
   attend_combine_kernel<<<H, 1024, 0, st>>>(part_o, part_l, n_cta, H, gmax, sink_scores,
-                                                static_cast<const __half*>(sink_v), n_sink, out);
+                                                static_cast<const __half*>(sink_v), n_sink, out, out_lse);
+  KVQ_LAUNCH_CHECK();
+  return 0;
+}
+
+int kvq_attend_merge(const float* parts, int n_parts, int H, float* out, void* stream) {
+  if (!parts || !out) return KVQ_E_NULL;
+  if (n_parts <= 0 || H <= 0) return KVQ_E_SHAPE;
+  attend_merge_kernel<<<H, kHeadDim, 0, static_cast<cudaStream_t>(stream)>>>(parts, n_parts, H, out);
   KVQ_LAUNCH_CHECK();
   return 0;
 }

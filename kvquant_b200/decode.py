@@ -67,7 +67,7 @@ def rmsnorm(x, w, eps):
 
 
 class DecoderLayer:
-    def __init__(self, cfg: DecodeConfig, device, gen, quantizer):
+    def __init__(self, cfg: DecodeConfig, device, gen, quantizer, with_sinks=True):
         h, it = cfg.hidden, cfg.intermediate
         def w(*shape):
             return (torch.randn(shape, generator=gen, device=device, dtype=torch.float32) * 0.02).half()
@@ -80,7 +80,7 @@ class DecoderLayer:
         self.cache = LayerCache.from_luts(cfg.bits, cfg.n_heads, cfg.max_len, quantizer["klut"], quantizer["v_cent"],
                                           device=device, include_sparse=cfg.include_sparse,
                                           sparsity_threshold=cfg.sparsity_threshold, n_sink=cfg.n_sink)
-        if cfg.n_sink:
+        if cfg.n_sink and with_sinks:
             sk = (torch.randn((cfg.n_heads, HEAD_DIM, cfg.n_sink), generator=gen, device=device)).half()
             sv = (torch.randn((cfg.n_heads, cfg.n_sink, HEAD_DIM), generator=gen, device=device)).half()
             self.cache.set_sinks(sk, sv)
@@ -89,12 +89,18 @@ class DecoderLayer:
 class DecoderStage:
     """Layers [lo, hi) of the model on one device, plus (first stage) the embedding and (rank 0) norm + lm_head."""
 
-    def __init__(self, cfg: DecodeConfig, lo: int, hi: int, device, quantizer, seed=0, with_head=True):
+    def __init__(self, cfg: DecodeConfig, lo: int, hi: int, device, quantizer, seed=0, with_head=True, sp=None):
+        """sp = (rank, world) switches to SEQUENCE-sharded attention: every rank holds all layers'
+        weights and a contiguous 1/world slice of every layer's cache; per layer the partial (out, lse) results are
+        all-gathered (H*129 floats per rank over NVLink) and merged.  The new token is appended on the last rank."""
         self.cfg, self.lo, self.hi = cfg, lo, hi
         self.device = torch.device(device)
+        self.sp = sp
+        self.global_pos = None   # sp: absolute position of the new token (set by the driver)
         gen = torch.Generator(device=self.device)
         gen.manual_seed(seed * 1000 + lo)
-        self.layers = [DecoderLayer(cfg, self.device, gen, quantizer) for _ in range(lo, hi)]
+        self.layers = [DecoderLayer(cfg, self.device, gen, quantizer, with_sinks=(sp is None or sp[0] == 0))
+                       for _ in range(lo, hi)]
         self.with_head = with_head
         if with_head:
             self.embed = (torch.randn((cfg.vocab, cfg.hidden), generator=gen, device=self.device) * 0.02).half()
@@ -128,6 +134,11 @@ class DecoderStage:
                              q=torch.empty(cfg.hidden, **f32), k=torch.empty(cfg.hidden, **f32),
                              v=torch.empty(cfg.hidden, **f32), o16=torch.empty(cfg.hidden, **f16),
                              gu=torch.empty(2 * cfg.intermediate, **f16), act=torch.empty(cfg.intermediate, **f16))
+            if self.sp is not None:
+                n = cfg.hidden + cfg.n_heads
+                self._buf["part"] = torch.empty(n, **f32)
+                self._buf["gath"] = torch.empty(self.sp[1] * n, **f32)
+                self._buf["om"] = torch.empty(cfg.hidden, **f32)
         return self._buf
 
     def forward(self, x):
@@ -142,13 +153,26 @@ class DecoderStage:
         st = torch.cuda.current_stream().cuda_stream
         for ly in self.layers:
             c = ly.cache
-            pos = c.n_sink + c.len                       # absolute position of the new token
+            # absolute position of the new token
+            pos = self.global_pos if self.sp is not None else c.n_sink + c.pos_base + c.len
             _lib.check(lib.kvq_dec_rmsnorm(x.data_ptr(), ly.n1.data_ptr(), b["h"].data_ptr(), hid, cfg.rms_eps, st))
             torch.mv(ly.wqkv, b["h"], out=b["qkv"])
             _lib.check(lib.kvq_dec_rope_split(b["qkv"].data_ptr(), self.inv_freq.data_ptr(), float(pos),
                                               b["q"].data_ptr(), b["k"].data_ptr(), b["v"].data_ptr(), hid, st))
-            c.append(b["k"], b["v"])                     # pre-RoPE K, per-token V: quantise + outlier split
-            o = c.attend(b["q"].view(H, HEAD_DIM), rope_theta=cfg.rope_theta)   # f32 [H,128]
+            if self.sp is None:
+                c.append(b["k"], b["v"])                 # pre-RoPE K, per-token V: quantise + outlier split
+                o = c.attend(b["q"].view(H, HEAD_DIM), rope_theta=cfg.rope_theta)   # f32 [H,128]
+            else:
+                import torch.distributed as dist
+                rank, world = self.sp
+                if rank == world - 1:
+                    c.append(b["k"], b["v"])             # the newest token lives on the last shard
+                part = b["part"]
+                c.attend(b["q"].view(H, HEAD_DIM), rope_theta=cfg.rope_theta, out=part[:hid].view(H, HEAD_DIM),
+                         lse=part[hid:])
+                dist.all_gather_into_tensor(b["gath"], part)      # H*129 floats per rank over NVLink
+                o = b["om"]
+                _lib.check(lib.kvq_attend_merge(b["gath"].data_ptr(), world, H, o.data_ptr(), st))
             _lib.check(lib.kvq_dec_f32_to_f16(o.data_ptr(), b["o16"].data_ptr(), hid, st))
             x = torch.addmv(x, ly.wo, b["o16"])
             _lib.check(lib.kvq_dec_rmsnorm(x.data_ptr(), ly.n2.data_ptr(), b["h"].data_ptr(), hid, cfg.rms_eps, st))
@@ -204,6 +228,11 @@ class GraphedStage:
             stage.set_len(L)
             y = stage.forward(x)
             return y
+
+        if stage.sp is not None:   # a few eager steps first so that NCCL is fully initialised before the capture
+            for _ in range(2):
+                body()
+            torch.cuda.synchronize(dev)
 
         # warm-up on a side stream (allocates scratch, sets func attributes, builds rope tables)
         s = torch.cuda.Stream(device=dev)

@@ -322,3 +322,32 @@ def test_error_codes_are_loud():
         _lib.check(-4, "x")
     # V / attend need Lmax % 4 == 0 (TMA row pitch)
     assert lib.kvq_v_matvec(4, z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 1, 32, 66, 8, None, None, 0, None) == -4
+
+
+def test_sequence_shard_merge_equals_single_attend():
+    """Sequence-sharded decode: two caches holding the two halves of the tokens, partial (out, lse)
+    results merged with kvq_attend_merge == one attend over everything."""
+    from kvquant_b200.cache import LayerCache
+    from kvquant_b200 import _lib
+    bits, L, H = 4, 900, 32
+    c, k, v = oracle_cache(bits, L)
+    klut, vcent = quantizer(bits)
+    q = cu(O.rope_rotate_q(spec().q_vec(12), L, 10000.0))
+    full = LayerCache.from_luts(bits, H, c.Lmax, klut, vcent, device=DEV)
+    full.load_state(c)
+    want = full.attend(q).clone()
+    cut = 448
+    parts = torch.zeros((2, H * 128 + H), device=DEV)
+    for r, (lo, hi) in enumerate(((0, cut), (cut, L))):
+        sh = LayerCache.from_luts(bits, H, 512, klut, vcent, device=DEV)
+        n = hi - lo
+        sh.kcache[:, :, :n] = full.kcache[:, :, lo:hi]; sh.vcache[:, :, :n] = full.vcache[:, :, lo:hi]
+        sh.vlut[:n] = full.vlut[lo:hi]; sh.vaff[:n] = full.vaff[lo:hi]
+        sh.k_outliers[:n] = full.k_outliers[lo:hi]; sh.k_outlier_idx[:n] = full.k_outlier_idx[lo:hi]
+        sh.v_outliers[:n] = full.v_outliers[lo:hi]; sh.v_outlier_idx[:n] = full.v_outlier_idx[lo:hi]
+        sh.len = n
+        sh.pos_base = lo
+        sh.attend(q, out=parts[r, :H * 128].view(H, 128), lse=parts[r, H * 128:])
+    out = torch.empty((H, 128), device=DEV)
+    _lib.check(_lib.load().kvq_attend_merge(parts.data_ptr(), 2, H, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    assert rel_err(out.cpu().numpy(), want.cpu().numpy())[0] < 1e-5
