@@ -10,9 +10,14 @@ fp16 of the LLaMA architecture, caches are filled with synthetic K/V through the
 The whole step is one CUDA graph; replays re-run the step at the SAME cache length (the fused append overwrites
 its slot), so all K timed steps are measured at the named seqlen.
 
-N > 1: layer-group pipeline (the reference's own multi-GPU scheme, modeling_llama.py:2428-2453), one process per
-GPU under torch.distributed (NCCL send/recv of the [hidden] fp16 vector over NVLink).  At batch 1 the stages run
-one after another, so this buys capacity, not tokens/sec -- reported as measured ("scaling": "strong").
+N > 1, one process per GPU under torch.distributed / NCCL, two layouts (--parallelism):
+  pp  layer-group pipeline -- the reference's own multi-GPU scheme (modeling_llama.py:2428-2453) and what north_star
+      prescribes: NCCL send/recv of the [hidden] fp16 vector over NVLink.  At batch 1 the stages run one after
+      another, so it buys capacity (1M-token contexts), not tokens/sec.
+  sp  sequence-sharded attention: weights replicated, every rank holds 1/N of every layer's
+      cache, per layer one all-gather of the partial (out, lse) results (H*129 floats per rank) and a merge kernel.
+      This is the layout in which decode speeds up with N; it is the default ("auto") when the workload divides.
+Both are strong scaling of the same fixed workload ("scaling": "strong").
 
 --impl reference: the reference's CPU implementation of the path, i.e. the C port of the kernel semantics
 (oracle/kvq_oracle_port.c; /root/reference does not exist on the GPU box and the reference's CPU path is Python)
@@ -149,9 +154,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--parallelism", default="pp", choices=["pp", "sp"],
-                    help="N>1: pp = layer-group pipeline (the reference's scheme, north_star); sp = sequence-sharded "
-                         "attention with replicated weights (SURVEY 8e-2 / 8f-1)")
+    ap.add_argument("--parallelism", default="auto", choices=["auto", "pp", "sp"],
+                    help="N>1: pp = layer-group pipeline (the reference's scheme, north_star: buys capacity, not "
+                         "tokens/sec at batch 1); sp = sequence-sharded attention with replicated weights (SURVEY 8e-2 / "
+                         "8f-1: the layout in which decode speeds up with N).  auto = sp when the workload fits, else pp")
     ap.add_argument("--torch-profile", default="", help="write a per-kernel table of 3 graph replays to this file (diagnostic)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -179,7 +185,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    sp_mode = (args.parallelism == "sp" and world > 1)
+    par = args.parallelism
+    if par == "auto":
+        par = "sp" if (world > 1 and L % world == 0) else "pp"
+    sp_mode = (par == "sp" and world > 1)
     if sp_mode and L % world:
         raise SystemExit("sp needs seq_len divisible by the number of GPUs")
     L_local = L // world if sp_mode else L
@@ -370,7 +379,13 @@ def main():
                     gpu_launches=int(launches_per_step * args.steps), roofline=roof, cpu_baseline=cpu_b)
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # tear-down: graphs that captured NCCL kernels must die before the communicator; a hung destroy must not hold
+        # the job (the result line is already out), so leave through os._exit after a final barrier
+        sys.stdout.flush()
+        del gs
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
     return 0
 
 
