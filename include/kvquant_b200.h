@@ -186,6 +186,14 @@ KVQ_API int kvq_dec_rope_split(const void* qkv_f16, const float* inv_freq, float
                                int hidden, void* stream);
 KVQ_API int kvq_dec_silu_mul(const void* gu_f16, void* act_f16, int n, void* stream);
 KVQ_API int kvq_dec_f32_to_f16(const float* a, void* b_f16, int n, void* stream);
+/* Batch-1 GEMV with its element-wise neighbours fused (replaces nn.Linear at q_len = 1, modeling_llama.py:1811-1813,
+ * 2004, and the norm / activation launch in front of it):  y[r] = residual[r] + sum_k W[r,k] * f(x)[k],
+ * W fp16 [N,K] row-major (16-byte aligned, K % 256 == 0, K <= 14336), fp32 accumulation.
+ * x_kind: 0 = fp16 [K]; 1 = f32 [K] (rounded through fp16 first); 2 = fp16 [2K] gate|up -> silu(gate)*up;
+ * 3 = fp16 [K] + HF LlamaRMSNorm with norm_w_f16 and eps.  residual_f16 may be NULL and may alias y; x must not.
+ * y is fp16 [N], or f32 [N] when y_f32 != 0. */
+KVQ_API int kvq_dec_gemv(const void* w_f16, int N, int K, const void* x, int x_kind, const void* norm_w_f16, float eps,
+                         const void* residual_f16, void* y, int y_f32, void* stream);
 
 #ifdef __cplusplus
 }

@@ -44,6 +44,7 @@ SIGNATURES = {
     "kvq_dec_rope_split": (_c_int, [_p, _p, _c_f, _p, _p, _p, _c_int, _p]),
     "kvq_dec_silu_mul": (_c_int, [_p, _p, _c_int, _p]),
     "kvq_dec_f32_to_f16": (_c_int, [_p, _p, _c_int, _p]),
+    "kvq_dec_gemv": (_c_int, [_p, _c_int, _c_int, _p, _c_int, _p, _c_f, _p, _p, _c_int, _p]),
 }
 
 _lib = None

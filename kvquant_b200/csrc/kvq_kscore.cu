@@ -17,7 +17,7 @@
 //     premultiplied tables T[h][c][code] = (LUT*q[h,c], s_c*LUT*q[h,c^64]) in shared memory: 16 (8, 4) entries per
 //     channel are 16 distinct consecutive 8-byte slots -> conflict-free multicast for any code pattern.
 //   * per element: 1 code extract, 1 LDS.64, 2 FFMA.
-#include "kvq_common.cuh"
+#include "kvq_kscore.cuh"
 #include <stdlib.h>
 
 namespace kvq {
@@ -32,40 +32,6 @@ template <int BITS> struct KCfg {
   static constexpr int D = (BITS == 4) ? 8 : 4;    // cp.async prefetch distance in (head, chunk) work items
 };
 
-struct KParams {
-  const float* q;            // [H,128]
-  const uint32_t* cache;     // [H*W, Lmax]
-  float* out;                // [H, out_stride]
-  const float* lut;          // [H*128, N]
-  const float* outliers;     // [>=L, n_out] or null (consumed by k_outlier_kernel, not by the dense kernel)
-  const int32_t* outlier_idx;
-  const float2* rope;        // [64, rope_npos]
-  float* gmax;               // [H] or null (fused mode: running max of scaled scores)
-  int64_t Lmax, L, out_stride, rope_npos;
-  int H, n_out, pos_offset, tiles_per_cta;
-  float scale;               // applied before the store (fused mode: 1/sqrt(128)); 1 for legacy
-  int accumulate;            // 1: out = (out + S)*scale, 0: out = S*scale
-};
-
-// compile-time loop (immediate LDS offsets and PRMT selectors need constant expressions)
-template <int K> struct IC { static constexpr int v = K; };
-template <int B, int E, class F>
-__device__ __forceinline__ void static_for(F&& f) {
-  if constexpr (B < E) { f(IC<B>{}); static_for<B + 1, E>(f); }
-}
-// 8-byte shared load at [addr + IMM] (addr is a 32-bit shared-window address)
-template <int IMM>
-__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
-  float2 v;
-  asm("ld.shared.v2.f32 {%0,%1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(addr), "n"(IMM));
-  return v;
-}
-// packed fp32 FMA (sm_100 FFMA2): acc.xy += a.xy * b.xy in one issue slot
-__device__ __forceinline__ void ffma2(float2& acc, const float2 a, const float2 b) {
-  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%0,%1};"
-      " fma.rn.f32x2 rc, ra, rb, rc; mov.b64 {%0,%1}, rc; }"
-      : "+f"(acc.x), "+f"(acc.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-}
 // 4-byte asynchronous global->shared copy (LDGSTS) with an L2 eviction policy; per-thread software pipeline
 __device__ __forceinline__ void cp_async4(uint32_t smem_dst, const void* gsrc, uint64_t pol, int pred) {
   asm volatile("{ .reg .pred p; setp.ne.s32 p, %3, 0;"
@@ -169,18 +135,20 @@ __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const
   __syncthreads();
   const uint32_t tab0 = smem_u32(s_tab);
 
-  // The CTA walks `tiles_per_cta` tiles of TT tokens; a thread's work items are linearised as
-  // (tile, chunk a = 0..7, head hl = 0..G-1); the packed words of item i+PD are loaded into a rotating register
-  // buffer while item i computes, the rope values of the next chunk likewise.
-  const int64_t tile_first = (int64_t)blockIdx.x * p.tiles_per_cta;
-  const int64_t tile_end = min(tile_first + p.tiles_per_cta, (p.L + TT - 1) / TT);
-  const int64_t t_limit = min(p.L, tile_end * TT);   // tokens this CTA may touch
+  // The CTA walks its token range [t_begin, t_limit) (a multiple of 32 tokens, cut so that every SM gets an equal
+  // share) in tiles of TT tokens; a thread's work items are linearised as (tile, chunk a = 0..7, head hl = 0..G-1);
+  // the packed words of item i+PD are loaded into a rotating register buffer while item i computes, the rope
+  // values of the next chunk likewise.  A warp whose 32 tokens lie past the range skips the (last) tile, so a
+  // partial tile costs only its live warps.
+  const int64_t t_begin = (int64_t)blockIdx.x * p.range;
+  const int64_t t_limit = min(p.L, t_begin + p.range);   // tokens this CTA may touch
+  if (t_begin >= t_limit) return;
   const uint32_t pitch = (uint32_t)p.Lmax * 4u;      // row pitch in bytes (host checks Lmax < 2^30)
   const unsigned char* cb0 = reinterpret_cast<const unsigned char*>(p.cache + (int64_t)h0 * W * p.Lmax);
 
   // pointers of the current / next tile's column for this thread, and whether those columns exist
-  const unsigned char* src_cur = cb0 + (tile_first * TT + tid) * 4;
-  bool ok_cur = (tile_first * TT + tid) < t_limit;
+  const unsigned char* src_cur = cb0 + (t_begin + tid) * 4;
+  bool ok_cur = (t_begin + tid) < t_limit;
 
   uint32_t wq[PD][NRW];   // rotating prefetch buffer (compile-time indices only)
 #pragma unroll
@@ -208,13 +176,14 @@ __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const
   float2 cs[8], csn[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { cs[k] = make_float2(0.f, 0.f); csn[k] = make_float2(0.f, 0.f); }
-  load_cs(cs, tile_first * TT + tid, 0);
+  load_cs(cs, t_begin + tid, 0);
 
-  for (int64_t tile = tile_first; tile < tile_end; ++tile) {
-    const int64_t t = tile * TT + tid;
-    const bool live = t < p.L;
+  for (int64_t tb = t_begin; tb < t_limit; tb += TT) {
+    const int64_t t = tb + tid;
+    const bool live = t < t_limit;
     const unsigned char* src_nxt = src_cur + TT * 4;
     const bool ok_nxt = (t + TT) < t_limit;
+    if (tb + (tid & ~31) < t_limit) {   // warp-uniform
     float2 acc[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) acc[g] = make_float2(0.f, 0.f);
@@ -233,7 +202,7 @@ __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const
         for (int i = 0; i < NRW; ++i) w[i] = wq[hl % PD][i];
         if constexpr (hl + PD < G) fetch(wq[hl % PD], src_cur, ok_cur, a, hl + PD);
         else fetch(wq[hl % PD], src_w, ok_w, a_w, hl + PD - G);
-        // no per-thread guard: lanes past L (and heads past nh) compute on zero / stale inputs and are dropped at the store
+        // no per-thread guard: lanes past the range (and heads past nh) compute on zero / stale inputs and are dropped at the store
         k_item<BITS>(w, a, tab0 + (uint32_t)hl * (kHeadDim * N * 8) + (uint32_t)a * (8 * N * 8), cs, acc[hl]);
       });
 #pragma unroll
@@ -257,6 +226,7 @@ __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const
           if ((tid & 31) == 0 && m > -INFINITY) atomic_max_float(p.gmax + h0 + hl, m);
         }
       }
+    }
     }
     src_cur = src_nxt;
     ok_cur = ok_nxt;
@@ -517,13 +487,8 @@ static int launch_k_kappa(const KParams& p, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Outlier pre-pass (replaces SPMV_ATOMIC_ROPE_BALANCED, quant_cuda_kernel.cu:472-521): thread = token, walks the
-// token's n_out (value, channel) pairs, RoPE evaluated with the reference's own expressions (theta from a 64-entry
-// powf table, cosf/sinf of theta*pos) -- 42 sincos per token instead of the dense path's former 4096.  The row is
-// sorted by channel, so contributions of one head are consecutive: they are summed in a register and written once
-// per head, without atomics (the thread owns column t of the score matrix in this launch).
-// store_all = 1: every head's entry is written (value or 0)  -> initialises the fused score buffer;
-// store_all = 0: only heads with outliers are touched, out += contribution (legacy accumulate semantics).
+// Outlier scatter (replaces SPMV_ATOMIC_ROPE_BALANCED, quant_cuda_kernel.cu:472-521).  Runs before the dense
+// kernel, which then folds `out` into its own sum: out = (out + S) * scale.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kOutThreads = 256;
 
@@ -568,6 +533,65 @@ __global__ void __launch_bounds__(kOutThreads) k_outlier_kernel(
   if (leader && e < total && contrib != 0.f) atomicAdd(out + (int64_t)h * out_stride + t, contrib);
 }
 
+// Persistent form (default).  ncu on the kernel above: load/store data path 75 % busy -- per ENTRY one scattered
+// 8-byte rope read plus TWO scattered reads of q.  Here CTAs are persistent and keep (q[c], q[c^64]) for all channels
+// in shared memory (one 8-byte shared read per entry instead of two scattered global ones); the rope values still
+// come from the table.  Measured alternatives: evaluating cosf/sinf(theta_j * pos) per entry
+// instead of the gather (50 us vs 55 us at 128K, 40 M instead of 26 M warp instructions), and accumulating into a
+// per-CTA [H][256-token] shared tile with coalesced write-out instead of global atomics (85-98 us: shared-memory
+// fp32 atomics are compare-and-swap loops).
+constexpr int kOutPersThreads = 512;
+__global__ void __launch_bounds__(kOutPersThreads) k_outlier_pers_kernel(
+    const float* __restrict__ q, const float* __restrict__ outliers, const int32_t* __restrict__ outlier_idx,
+    float* __restrict__ out, int64_t out_stride, int64_t L, int H, int n_out, const float2* __restrict__ rope,
+    int64_t rope_npos, int pos_offset, float scale) {
+  extern __shared__ float2 s_qq[];                       // [H*128] = (q[c], q[c^64])
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < H * kHeadDim; i += kOutPersThreads) s_qq[i] = make_float2(q[i], q[i ^ kHalf]);
+  __syncthreads();
+  const uint32_t total = (uint32_t)(L * n_out);          // host checks L * n_out < 2^31
+  const uint32_t stride = gridDim.x * kOutPersThreads;
+  const uint64_t pol_keep = policy_evict_last();
+  for (uint32_t base = blockIdx.x * kOutPersThreads + (tid & ~31); base < total; base += stride) {
+    const uint32_t e = base + lane;
+    float contrib = 0.f;
+    int key = -1 - lane;   // unique negative keys for idle lanes (never merge)
+    uint32_t t = 0;
+    int h = 0;
+    if (e < total) {
+      t = e / (uint32_t)n_out;
+      const float v = outliers[e];
+      const int col = outlier_idx[e];
+      h = col >> 7;
+      const int c = col & (kHeadDim - 1);
+      key = (int)(t * 64u) + h;                          // t < 2^25
+      if (v != 0.f) {   // pads / non-outliers contribute exactly 0 in the reference too
+        const float2 cs = ld_keep_f2(rope + (int64_t)(c & (kHalf - 1)) * rope_npos + t + pos_offset, pol_keep);
+        const float2 qq = s_qq[col];
+        const float sign = (c < kHalf) ? 1.f : -1.f;
+        float dot = v * cs.x * qq.x;            // same operation order as DK.cu:513-515
+        dot += sign * v * cs.y * qq.y;
+        contrib = dot * scale;
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float v2 = __shfl_down_sync(0xffffffffu, contrib, o);
+      const int k2 = __shfl_down_sync(0xffffffffu, key, o);
+      if (lane + o < 32 && k2 == key) contrib += v2;
+    }
+    const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool leader = (lane == 0) || (kprev != key);
+    if (leader && e < total && contrib != 0.f) atomicAdd(out + (int64_t)h * out_stride + t, contrib);
+  }
+}
+
+static int k_out_impl_table() {   // KVQ_KOUT_IMPL=table selects the non-persistent gather form for A/B runs
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("KVQ_KOUT_IMPL"); v = (e && e[0] == 't') ? 1 : 0; }
+  return v;
+}
+
 // zero_first = 1: `out` is a fresh score buffer (fused path) and is cleared before the scatter
 static int launch_k_outliers(const KParams& p, int zero_first, float scale, cudaStream_t st) {
   if (zero_first) {
@@ -575,9 +599,28 @@ static int launch_k_outliers(const KParams& p, int zero_first, float scale, cuda
     if (e != cudaSuccess) return (int)e;
   }
   const int64_t total = p.L * p.n_out;
-  const unsigned grid = (unsigned)((total + kOutThreads - 1) / kOutThreads);
-  k_outlier_kernel<<<grid, kOutThreads, 0, st>>>(p.q, p.outliers, p.outlier_idx, p.out, p.out_stride, p.L, p.H,
-                                                 p.n_out, p.rope, p.rope_npos, p.pos_offset, scale);
+  const size_t smem = (size_t)p.H * kHeadDim * sizeof(float2);
+  if (k_out_impl_table() || smem > 100 * 1024 || total >= ((int64_t)1 << 31) || p.L >= ((int64_t)1 << 25)) {
+    const unsigned grid = (unsigned)((total + kOutThreads - 1) / kOutThreads);
+    k_outlier_kernel<<<grid, kOutThreads, 0, st>>>(p.q, p.outliers, p.outlier_idx, p.out, p.out_stride, p.L, p.H,
+                                                   p.n_out, p.rope, p.rope_npos, p.pos_offset, scale);
+    KVQ_LAUNCH_CHECK();
+    return 0;
+  }
+  static size_t smem_set = 48 * 1024;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_outlier_pers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    smem_set = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = (total + kOutPersThreads - 1) / kOutPersThreads;
+  const int per_sm = smem > 56 * 1024 ? 2 : 4;
+  const unsigned grid = (unsigned)(want < (int64_t)sms * per_sm ? want : (int64_t)sms * per_sm);
+  k_outlier_pers_kernel<<<grid, kOutPersThreads, smem, st>>>(p.q, p.outliers, p.outlier_idx, p.out, p.out_stride, p.L,
+                                                             p.H, p.n_out, p.rope, p.rope_npos, p.pos_offset, scale);
   KVQ_LAUNCH_CHECK();
   return 0;
 }
@@ -609,14 +652,13 @@ static int launch_k_scores(const KParams& p, cudaStream_t st) {
     attr_done = true;
   }
   const int n_groups = (p.H + C::G - 1) / C::G;
-  const int64_t n_tiles = (p.L + C::TT - 1) / C::TT;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t max_splits = sms / n_groups > 0 ? sms / n_groups : 1;
   KParams q = p;
-  q.tiles_per_cta = (int)((n_tiles + max_splits - 1) / max_splits);
-  const int64_t splits = (n_tiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
+  q.range = k_token_range(p.L, max_splits);
+  const int64_t splits = (p.L + q.range - 1) / q.range;
   const dim3 grid((unsigned)splits, (unsigned)n_groups);
   if (p.H % C::G == 0) k_scores_kernel<BITS, true><<<grid, C::kThreads, smem, st>>>(q);
   else k_scores_kernel<BITS, false><<<grid, C::kThreads, smem, st>>>(q);
@@ -624,16 +666,23 @@ static int launch_k_scores(const KParams& p, cudaStream_t st) {
   return 0;
 }
 
-static int k_impl_lds64() {
-  // default: the LDS.64 form (measured faster on B200: 197 us vs 253 us for 4-bit / 128K, profiles/r01_*);
-  // KVQ_K_IMPL=kappa selects the 4-byte-entry kappa form for A/B runs
+// KVQ_K_IMPL selects the dense kernel for A/B runs.  Default: 4-bit / 2-bit -> k_scores_kernel (this file),
+// 3-bit -> k_scores3_kernel (kvq_k3.cu).  "generic": k_scores_kernel for every width; "pair": pair-table form
+// (kvq_kpair.cu, 4/3-bit); "kappa": 4-byte entries + constant-bank q.  Measurements: DESIGN.md section 4.1.
+static int k_impl() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("KVQ_K_IMPL"); v = (e && e[0] == 'k') ? 0 : 1; }
+  if (v < 0) {
+    const char* e = getenv("KVQ_K_IMPL");
+    v = !e ? 0 : (e[0] == 'g' ? 1 : (e[0] == 'p' ? 2 : (e[0] == 'k' ? 3 : 0)));
+  }
   return v;
 }
 
 int k_scores_dispatch(int bits, const KParams& p, cudaStream_t st) {
-  if (p.H <= kMaxConstHeads && !k_impl_lds64()) {
+  const int impl = k_impl();
+  if (impl == 0 && bits == 3) return k_scores3_dispatch(p, st);
+  if (impl == 2 && (bits == 4 || bits == 3)) return k_pair_dispatch(bits, p, st);
+  if (impl == 3 && p.H <= kMaxConstHeads) {
     switch (bits) {
       case 4: return launch_k_kappa<4>(p, st);
       case 3: return launch_k_kappa<3>(p, st);
@@ -657,7 +706,7 @@ int k_scores_fused(int bits, const float* q, const int32_t* cache, float* scores
   p.q = q; p.cache = reinterpret_cast<const uint32_t*>(cache); p.out = scores; p.lut = lut;
   p.outliers = outliers; p.outlier_idx = outlier_idx; p.rope = reinterpret_cast<const float2*>(rope);
   p.gmax = gmax; p.Lmax = Lmax; p.L = L; p.out_stride = score_stride; p.rope_npos = rope_npos;
-  p.H = H; p.n_out = n_out; p.pos_offset = pos_offset; p.scale = scale; p.accumulate = 0;
+  p.H = H; p.n_out = n_out; p.pos_offset = pos_offset; p.scale = scale; p.accumulate = 0; p.theta = theta;
   if (outliers != nullptr) {
     // outlier contributions are deposited UNSCALED (the dense kernel applies `scale` to out + S)
     const int rc = launch_k_outliers(p, /*zero_first=*/1, 1.f, st);
@@ -703,7 +752,7 @@ int kvq_k_matvec(int bits, const float* q, const int32_t* cache, float* mul, con
     p.gmax = nullptr;
     p.Lmax = Lmax; p.L = L; p.out_stride = L; p.rope_npos = rope_npos;
     p.H = H; p.n_out = n_out; p.pos_offset = pos_offset;
-    p.scale = 1.f; p.accumulate = 1;
+    p.scale = 1.f; p.accumulate = 1; p.theta = theta;
     if (outliers != nullptr) {
       const int rc0 = launch_k_outliers(p, /*zero_first=*/0, 1.f, static_cast<cudaStream_t>(stream));
       if (rc0 != 0) return rc0;

@@ -358,27 +358,41 @@ __global__ void attend_init_kernel(const float* __restrict__ q, const __half* __
 }
 
 // out[h,c] = (sum_s o[s,h,c] + sum_i p_i * sink_v[h,i,c]) / (sum_s l[s,h] + sum_i p_i),  p_i = exp(sink_s[h,i]-max)
-// grid = H, block = 1024: 8 slices of the partials x 128 channels, reduced through shared memory
+// grid = H, block = 1024: 32 slices of the partials (one warp each, a lane owns 4 channels: 16-byte loads, all of a
+// thread's <= 8 loads in flight at once), reduced through shared memory
 __global__ void __launch_bounds__(1024) attend_combine_kernel(const float* __restrict__ po, const float* __restrict__ pl,
                                                               int n_part, int H, const float* __restrict__ gmax,
                                                               const float* __restrict__ sink_scores,
                                                               const __half* __restrict__ sink_v, int n_sink,
                                                               float* __restrict__ out, float* __restrict__ out_lse) {
-  __shared__ float s_o[8][kHeadDim];
-  __shared__ float s_l[8];
-  const int h = blockIdx.x, c = threadIdx.x & (kHeadDim - 1), g = threadIdx.x >> 7;
-  float o = 0.f, l = 0.f;
-  for (int s = g; s < n_part; s += 8) {
-    o += po[((int64_t)s * H + h) * kHeadDim + c];
-    if (c == 0) l += pl[(int64_t)s * H + h];
-  }
-  s_o[g][c] = o;
-  if (c == 0) s_l[g] = l;
-  __syncthreads();
-  if (g != 0) return;
-  o = 0.f; l = 0.f;
+  __shared__ float4 s_o[32][32];
+  __shared__ float s_l[32];
+  const int h = blockIdx.x, lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float lsum = 0.f;
+  constexpr int kU = 8;   // n_part <= 256 partials -> at most 8 per slice
+  float4 v[kU];
+  float lv[kU];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { o += s_o[i][c]; l += s_l[i]; }
+  for (int i = 0; i < kU; ++i) {
+    const int s = g + 32 * i;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    lv[i] = 0.f;
+    if (s < n_part) {
+      v[i] = __ldcg(reinterpret_cast<const float4*>(po + ((int64_t)s * H + h) * kHeadDim) + lane);
+      if (lane == 0) lv[i] = __ldcg(pl + (int64_t)s * H + h);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kU; ++i) { o4.x += v[i].x; o4.y += v[i].y; o4.z += v[i].z; o4.w += v[i].w; lsum += lv[i]; }
+  s_o[g][lane] = o4;
+  if (lane == 0) s_l[g] = lsum;
+  __syncthreads();
+  if (threadIdx.x >= kHeadDim) return;
+  const int c = threadIdx.x;
+  float o = 0.f, l = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { o += reinterpret_cast<const float*>(&s_o[i][0])[c]; l += s_l[i]; }
   const float m = gmax[h];
   for (int i = 0; i < n_sink; ++i) {
     const float pi = __expf(sink_scores[h * 64 + i] - m);

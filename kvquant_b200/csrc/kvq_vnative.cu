@@ -53,7 +53,7 @@ __host__ __device__ inline VNSmem vn_smem_layout(int rows, int tabn, int H, int 
   s.off_w = s.off_tab + (uint32_t)tabn * 256u;
   s.off_ws = s.off_w + 2u * H * kNT * 4;
   s.off_oacc = s.off_ws + 2u * H * kNT * 4;
-  s.off_bar = s.off_oacc + (uint32_t)H * kHeadDim * 4;
+  s.off_bar = s.off_oacc;   // (the outlier accumulator lives in the partial-output row in global memory)
   s.total = s.off_bar + 8u * kNMaxStages;
   return s;
 }
@@ -62,6 +62,9 @@ __device__ __forceinline__ float2 lds_f2_dyn(uint32_t addr) {
   float2 v;
   asm("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
   return v;
+}
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+  asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ void ffma2v(float2& acc, const float2 a, const float2 b) {
   asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%0,%1};"
@@ -125,7 +128,6 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
   float2* s_tab = reinterpret_cast<float2*>(smem + lay.off_tab);   // [TABN][32 lanes]
   float* s_w = reinterpret_cast<float*>(smem + lay.off_w);         // [2][H][16]   w = exp(s - max)
   float* s_ws = reinterpret_cast<float*>(smem + lay.off_ws);       // [2][H][16]   w * sf_t
-  float* s_oacc = reinterpret_cast<float*>(smem + lay.off_oacc);   // [H*128]
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + lay.off_bar);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -184,7 +186,13 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
 #pragma unroll
     for (int k = 0; k < NP; ++k) acc[i][k] = make_float2(0.f, 0.f);
 
-  for (int i = tid; i < hidden; i += kNThreads) s_oacc[i] = 0.f;
+  // this CTA's row of the partial-output buffer doubles as the outlier accumulator: cleared here, reduced into by
+  // the outlier rows, read back (after a fence) and completed in the epilogue
+  float* obase = p.out_o + (int64_t)blockIdx.x * hidden;
+  if (p.outliers != nullptr) {
+    for (int i = tid; i < hidden; i += kNThreads) obase[i] = 0.f;
+    __threadfence();   // the clears reach L2 before any reduction (ordered by the __syncthreads below)
+  }
   if (tid == 0) {
     for (int s = 0; s < S; ++s) mbar_init(&s_bar[s], 1);
     mbar_fence_init();
@@ -246,7 +254,11 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
       if (e < n_w) { s_w[buf * n_w + e] = wpre[i]; s_ws[buf * n_w + e] = wspre[i]; }
     }
   };
-  // outliers: warp w owns tokens {w, w+16} of the tile; lanes walk the row (no divisions), prefetched into registers
+  // outliers: O[j] += w[h(j), t] * val(t, j).  Warp w owns tokens {w, w+16} of the tile; lanes walk the row (no
+  // divisions), prefetched into registers.  The sums go straight to this CTA's row of the partial-output buffer with
+  // fire-and-forget global reductions (RED.ADD.F32): shared memory has no native fp32 atomic add -- atomicAdd on
+  // shared compiles to a compare-and-swap loop that ncu charged with 55 % of this kernel's shared-memory
+  // wavefronts, more than the table lookups -- whereas a RED costs one L1 pass per lane and no return trip.
   constexpr int NO = 2 * kNTokPerWarp;   // (value, index) pairs per lane per tile for n_out <= 64
   float opre_v[NO];
   int opre_i[NO];
@@ -308,7 +320,7 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
           const float v = opre_v[2 * j + r];
           if (v != 0.f) {
             const int idx = opre_i[2 * j + r];
-            atomicAdd(&s_oacc[idx], v * wbuf[(idx >> 7) * kNT + tl]);
+            red_add_f32(obase + idx, v * wbuf[(idx >> 7) * kNT + tl]);
           }
         }
         for (int k = lane + 64; k < p.n_out; k += 32) {   // n_out > 64: unprefetched tail
@@ -316,13 +328,14 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
           if (t < p.L) {
             const float v = p.outliers[t * p.n_out + k];
             const int idx = p.outlier_idx[t * p.n_out + k];
-            if (v != 0.f) atomicAdd(&s_oacc[idx], v * wbuf[(idx >> 7) * kNT + tl]);
+            if (v != 0.f) red_add_f32(obase + idx, v * wbuf[(idx >> 7) * kNT + tl]);
           }
         }
       }
     }
     if (more) { finish_weights(); store_weights((it + 1) & 1); }
   }
+  __threadfence();   // this thread's reductions are performed at L2 before anyone reads the row back
   __syncthreads();
 
   // ---- epilogue: per-head scalars (denominator, offset term), then the partial output -----------------------------
@@ -339,7 +352,6 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
   }
   __syncthreads();
   for (int i = tid; i < p.H; i += kNThreads) p.out_l[(int64_t)blockIdx.x * p.H + i] = s_l[i];
-  float* obase = p.out_o + (int64_t)blockIdx.x * hidden;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     if (u_on[i]) {
@@ -350,7 +362,7 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
         if (k < nch) {
           const int j = u_head[i] * kHeadDim + u_ch0[i] + k;
           const float v = (k & 1) ? acc[i][k >> 1].y : acc[i][k >> 1].x;
-          obase[j] = v + hoff + s_oacc[j];
+          obase[j] = v + hoff + (has_out ? __ldcg(obase + j) : 0.f);
         }
       }
     }

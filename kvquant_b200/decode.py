@@ -115,6 +115,8 @@ class DecoderStage:
         return self.embed[tok].view(-1)
 
     def head(self, x):
+        if x.is_cuda:
+            return self._gemv(self.lm_head, x, 3, self._buffers()["logits"], norm_w=self.norm)
         return self.lm_head @ rmsnorm(x, self.norm, self.cfg.rms_eps)
 
     def _rope_q(self, q, pos):
@@ -133,7 +135,9 @@ class DecoderStage:
             self._buf = dict(h=torch.empty(cfg.hidden, **f16), qkv=torch.empty(3 * cfg.hidden, **f16),
                              q=torch.empty(cfg.hidden, **f32), k=torch.empty(cfg.hidden, **f32),
                              v=torch.empty(cfg.hidden, **f32), o16=torch.empty(cfg.hidden, **f16),
-                             gu=torch.empty(2 * cfg.intermediate, **f16), act=torch.empty(cfg.intermediate, **f16))
+                             gu=torch.empty(2 * cfg.intermediate, **f16), act=torch.empty(cfg.intermediate, **f16),
+                             x0=torch.empty(cfg.hidden, **f16), x1=torch.empty(cfg.hidden, **f16),
+                             logits=torch.empty(cfg.vocab, **f16))
             if self.sp is not None:
                 n = cfg.hidden + cfg.n_heads
                 self._buf["part"] = torch.empty(n, **f32)
@@ -141,22 +145,35 @@ class DecoderStage:
                 self._buf["om"] = torch.empty(cfg.hidden, **f32)
         return self._buf
 
+    def _gemv(self, w, x, kind, y, norm_w=None, residual=None):
+        """y = residual + w @ f(x) through the library's fused GEMV (kvq_dec_gemv); kind: 0 fp16, 1 f32, 2 gate|up
+        -> silu(gate)*up, 3 fp16 + RMSNorm(norm_w)."""
+        from . import _lib
+        lib = _lib.load()
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.kvq_dec_gemv(w.data_ptr(), w.shape[0], w.shape[1], x.data_ptr(), kind,
+                                    norm_w.data_ptr() if norm_w is not None else None, self.cfg.rms_eps,
+                                    residual.data_ptr() if residual is not None else None, y.data_ptr(), 0, st))
+        return y
+
     def forward(self, x):
         """x: fp16 [hidden] -> fp16 [hidden] after this stage's layers; appends one token to every layer cache.
-        GEMVs are cuBLAS (torch.mv / addmv); RMSNorm, RoPE+split, SwiGLU and the cast are fused helper kernels of the
-        library (kvq_dec_*), everything touching the KV cache is kvq_append_kv_fused + kvq_attend."""
+        Four launches per layer outside the KV cache: GEMV(+RMSNorm) -> RoPE/split -> [append, attend] ->
+        GEMV(+residual) -> GEMV(+RMSNorm) -> GEMV(SwiGLU input, +residual); everything touching the KV cache is
+        kvq_append_kv_fused + kvq_attend."""
         from . import _lib
         cfg = self.cfg
         lib = _lib.load()
         b = self._buffers()
-        H, hid, it = cfg.n_heads, cfg.hidden, cfg.intermediate
+        H, hid = cfg.n_heads, cfg.hidden
         st = torch.cuda.current_stream().cuda_stream
+        xs = (b["x0"], b["x1"])     # ping-pong residual stream (the caller's x is never written)
+        flip = 0
         for ly in self.layers:
             c = ly.cache
             # absolute position of the new token
             pos = self.global_pos if self.sp is not None else c.n_sink + c.pos_base + c.len
-            _lib.check(lib.kvq_dec_rmsnorm(x.data_ptr(), ly.n1.data_ptr(), b["h"].data_ptr(), hid, cfg.rms_eps, st))
-            torch.mv(ly.wqkv, b["h"], out=b["qkv"])
+            self._gemv(ly.wqkv, x, 3, b["qkv"], norm_w=ly.n1)
             _lib.check(lib.kvq_dec_rope_split(b["qkv"].data_ptr(), self.inv_freq.data_ptr(), float(pos),
                                               b["q"].data_ptr(), b["k"].data_ptr(), b["v"].data_ptr(), hid, st))
             if self.sp is None:
@@ -173,12 +190,11 @@ class DecoderStage:
                 dist.all_gather_into_tensor(b["gath"], part)      # H*129 floats per rank over NVLink
                 o = b["om"]
                 _lib.check(lib.kvq_attend_merge(b["gath"].data_ptr(), world, H, o.data_ptr(), st))
-            _lib.check(lib.kvq_dec_f32_to_f16(o.data_ptr(), b["o16"].data_ptr(), hid, st))
-            x = torch.addmv(x, ly.wo, b["o16"])
-            _lib.check(lib.kvq_dec_rmsnorm(x.data_ptr(), ly.n2.data_ptr(), b["h"].data_ptr(), hid, cfg.rms_eps, st))
-            torch.mv(ly.wgu, b["h"], out=b["gu"])
-            _lib.check(lib.kvq_dec_silu_mul(b["gu"].data_ptr(), b["act"].data_ptr(), it, st))
-            x = torch.addmv(x, ly.wdown, b["act"])
+            x = self._gemv(ly.wo, o, 1, xs[flip], residual=x)
+            flip ^= 1
+            self._gemv(ly.wgu, x, 3, b["gu"], norm_w=ly.n2)
+            x = self._gemv(ly.wdown, b["gu"], 2, xs[flip], residual=x)
+            flip ^= 1
         return x
 
     def forward_torch(self, x):
