@@ -146,6 +146,20 @@ def cpu_baseline_run(layer_arrays, bits, H, Lmax, L, n_out, n_layers, theta, pos
         "extrapolated to %d layers x %d tokens; GEMVs excluded" % (Ls, L, n_layers, L)
 
 
+def ncu_traffic(bits, L):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one fused attend (all its kernels), per launch, from the
+    committed ncu --set full capture of the same shape (profiles/ncu_traffic.json); None when no capture matches."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            for e in json.load(f)["entries"]:
+                if e["bits"] == bits and abs(e["L"] - L) <= 1024:
+                    return e["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -158,6 +172,9 @@ def main():
                     help="N>1: pp = layer-group pipeline (the reference's scheme, north_star: buys capacity, not "
                          "tokens/sec at batch 1); sp = sequence-sharded attention with replicated weights (SURVEY 8e-2 / "
                          "8f-1: the layout in which decode speeds up with N).  auto = sp when the workload fits, else pp")
+    ap.add_argument("--graph", default="dynamic", choices=["dynamic", "static"],
+                    help="dynamic: cache length / position live on the device and every replay is the NEXT decode step "
+                         "(growing cache); static: every replay re-runs the step at the captured length")
     ap.add_argument("--torch-profile", default="", help="write a per-kernel table of 3 graph replays to this file (diagnostic)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -192,12 +209,16 @@ def main():
     if sp_mode and L % world:
         raise SystemExit("sp needs seq_len divisible by the number of GPUs")
     L_local = L // world if sp_mode else L
-    cfg = kd.DecodeConfig.llama7b(bits=bits, n_sink=n_sink, max_len=L_local + 64)
+    # room for every step this run appends (warm-up + profile + timed, device and e2e loops)
+    headroom = (2 * (args.steps + args.warmup) + 3 + 8 + 63) // 64 * 64
+    cfg = kd.DecodeConfig.llama7b(bits=bits, n_sink=n_sink, max_len=L_local + headroom)
     sp, quantizer = build_quantizer(bits, cfg.n_heads, dev)
     config = {"workload": args.workload, "description": desc, "bits": bits, "seq_len": L + n_sink, "n_sink": n_sink,
               "outliers": "1% (21+21 per token per cache)", "layers": cfg.n_layers, "parallelism": ("sp%d" if sp_mode else "pp%d") % world,
               "l2_policy": "inputs larger than L2: every step streams all layers' caches (>= 4 GB) and 13.5 GB of weights",
-              "step": "one CUDA-graph replay of a full decode step at fixed cache length"}
+              "step": ("one CUDA-graph replay = the next decode step of a growing cache (length and position live in "
+                       "device memory; step i appends slot L+i and attends over L+i+1 slots)") if args.graph == "dynamic"
+              else "one CUDA-graph replay of a full decode step at fixed cache length"}
 
     # ---------------------------------------------------------------------------------------------------------
     if args.impl == "reference":
@@ -241,7 +262,8 @@ def main():
     t_fill = time.time() - t_fill
 
     n0 = _lib.launch_count()
-    gs = kd.GraphedStage(stage, L_local, first=(rank == 0 or sp_mode), last_to_logits=(world == 1 or sp_mode))
+    gs = kd.GraphedStage(stage, L_local, first=(rank == 0 or sp_mode), last_to_logits=(world == 1 or sp_mode),
+                         dynamic=(args.graph == "dynamic"), pos=(n_sink + L) if sp_mode else None)
     launches_per_step = (_lib.launch_count() - n0) // (5 if sp_mode else 3)   # eager warm-up passes + 1 capture pass
     if world > 1 and rank == 0:
         head_graph_in = torch.zeros(cfg.hidden, dtype=torch.float16, device=dev)
@@ -336,7 +358,7 @@ def main():
             torch.cuda.synchronize()
             return a.elapsed_time(b) / (reps * len(layers))
 
-        Lq = L_local + (0 if (sp_mode and rank != world - 1) else 1)
+        Lq = layers[0].cache.len      # current length (the timed steps appended to the cache)
         ms_att = time_loop(lambda ly: ly.cache.attend(q, rope_theta=cfg.rope_theta))
         from kvquant_b200 import quant_cuda as qc
         mulK = torch.zeros((1, cfg.n_heads, Lq), device=dev)
@@ -354,8 +376,10 @@ def main():
         b_k = Lq * (cfg.hidden * bits // 8 + 8 * n_out)
         b_v = Lq * (cfg.hidden * bits // 8 + 8 * n_out + 4 * 2 ** bits)
         ach = b_att / ms_att / 1e6
-        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "peak_source": peak_src, "kernel": "kvq_attend = attend_init + k_scores_kernel + v_accum_kernel + attend_combine",
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": ncu_traffic(bits, Lq),
+                "peak_source": peak_src,
+                "kernel": "kvq_attend = attend_init + k_outlier_pers + k_scores(3) + v_native + attend_combine",
                 "algorithmic_bytes_per_launch": b_att, "ms_per_launch": ms_att,
                 "per_kernel": {"k_scores_kernel": {"ms": ms_k, "bytes": b_k, "gbs": b_k / ms_k / 1e6, "frac": b_k / ms_k / 1e6 / peak},
                                "v_accum_kernel": {"ms": ms_v, "bytes": b_v, "gbs": b_v / ms_v / 1e6, "frac": b_v / ms_v / 1e6 / peak}},

@@ -135,6 +135,29 @@ KVQ_API int kvq_attend(int bits, const float* q,
 KVQ_API int kvq_attend_merge(const float* parts, int n_parts, int H, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Device-resident cache length: the same operations with the length read from device memory at
+ * run time, so that ONE captured CUDA graph serves a growing cache -- the reference re-reads klen / vlen on the host
+ * every step (modeling_llama.py:791, 1215).  len_dev points at an int64 that the caller advances (e.g. with
+ * kvq_dec_counter_add at the end of the captured step).
+ *   kvq_append_kv_fused_dyn : writes slot  *len_dev + slot_add  (a full cache drops the token)
+ *   kvq_attend_dyn          : attends over L = min(*len_dev + len_add, L_cap) slots; grids, scratch
+ *                             (kvq_attend_scratch_bytes(H, L_cap)) and the rope table are sized for L_cap.
+ *                             Native V form only (v_cent + v_aff); KVQ_E_UNSUPPORTED where kvq_attend would fall back.
+ * ------------------------------------------------------------------------------------------------------------- */
+KVQ_API int kvq_append_kv_fused_dyn(int bits, int H, int64_t Lmax, const int64_t* len_dev, int64_t slot_add, int n_each,
+                            const float* k_new, int32_t* kcache, const float* klut, const float* klut_sub,
+                            const float* k_thr_lower, const float* k_thr_upper, float* k_outliers,
+                            int32_t* k_outlier_idx, const float* v_new, int32_t* vcache, const float* v_cent,
+                            const float* v_cent_deq, float* vlut_tok, float* v_aff, float* v_outliers,
+                            int32_t* v_outlier_idx, void* stream);
+KVQ_API int kvq_attend_dyn(int bits, const float* q, const int32_t* kcache, const float* klut, const float* k_outliers,
+                   const int32_t* k_outlier_idx, const int32_t* vcache, const float* v_cent, const float* v_aff,
+                   const float* v_outliers, const int32_t* v_outlier_idx, int n_out, int H, int64_t Lmax, int64_t L_cap,
+                   const int64_t* len_dev, int64_t len_add, const float* rope_cos_sin, int64_t rope_npos, float theta,
+                   int pos_offset, const void* sink_k, const void* sink_v, int n_sink, float* out, float* out_lse,
+                   void* scratch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Fused device-side append (native op): replaces the whole host round trip of
  * QuantK/QuantV.forward_fused_sparse (modeling_llama.py:664-751, 1803-1820, 1091-1176): append kernel +
  * .cpu() + torch.topk + gather/mask/sort + row writes, for K and V of one token, in one launch, no host sync.
@@ -184,6 +207,11 @@ KVQ_API int kvq_append_v_orig(int32_t* cache, const float* lut_tok, const float*
 KVQ_API int kvq_dec_rmsnorm(const void* x_f16, const void* w_f16, void* y_f16, int n, float eps, void* stream);
 KVQ_API int kvq_dec_rope_split(const void* qkv_f16, const float* inv_freq, float pos, float* q, float* k, float* v,
                                int hidden, void* stream);
+/* q RoPE position = *pos_dev + pos_add (device-resident, see kvq_attend_dyn) */
+KVQ_API int kvq_dec_rope_split_dyn(const void* qkv_f16, const float* inv_freq, const int64_t* pos_dev, int64_t pos_add,
+                                   float* q, float* k, float* v, int hidden, void* stream);
+/* *counter += delta on the stream (advances the device-resident length / position inside a captured step) */
+KVQ_API int kvq_dec_counter_add(int64_t* counter, int64_t delta, void* stream);
 KVQ_API int kvq_dec_silu_mul(const void* gu_f16, void* act_f16, int n, void* stream);
 KVQ_API int kvq_dec_f32_to_f16(const float* a, void* b_f16, int n, void* stream);
 /* Batch-1 GEMV with its element-wise neighbours fused (replaces nn.Linear at q_len = 1, modeling_llama.py:1811-1813,

@@ -36,12 +36,18 @@ SIGNATURES = {
     "kvq_attend_merge": (_c_int, [_p, _c_int, _c_int, _p, _p]),
     "kvq_append_kv_fused": (_c_int, [_c_int, _c_int, _c_i64, _c_i64, _c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                      _p, _p, _p, _p, _p, _p, _p]),
+    "kvq_append_kv_fused_dyn": (_c_int, [_c_int, _c_int, _c_i64, _p, _c_i64, _c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p,
+                                         _p, _p, _p, _p, _p, _p, _p, _p]),
+    "kvq_attend_dyn": (_c_int, [_c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_i64, _c_i64, _p,
+                                _c_i64, _p, _c_i64, _c_f, _c_int, _p, _p, _c_int, _p, _p, _p, _p]),
     "kvq_k_spmv_csr": (_c_int, [_p, _p, _p, _p, _p, _p, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_f, _c_int, _p]),
     "kvq_v_spmv_csc": (_c_int, [_p, _p, _p, _p, _p, _p, _c_int, _c_i64, _c_int, _c_int, _c_int, _p]),
     "kvq_append_k_orig": (_c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_i64, _c_i64, _p]),
     "kvq_append_v_orig": (_c_int, [_p, _p, _p, _c_f, _c_f, _c_f, _p, _p, _p, _c_int, _c_i64, _c_i64, _p]),
     "kvq_dec_rmsnorm": (_c_int, [_p, _p, _p, _c_int, _c_f, _p]),
     "kvq_dec_rope_split": (_c_int, [_p, _p, _c_f, _p, _p, _p, _c_int, _p]),
+    "kvq_dec_rope_split_dyn": (_c_int, [_p, _p, _p, _c_i64, _p, _p, _p, _c_int, _p]),
+    "kvq_dec_counter_add": (_c_int, [_p, _c_i64, _p]),
     "kvq_dec_silu_mul": (_c_int, [_p, _p, _c_int, _p]),
     "kvq_dec_f32_to_f16": (_c_int, [_p, _p, _c_int, _p]),
     "kvq_dec_gemv": (_c_int, [_p, _c_int, _c_int, _p, _c_int, _p, _c_f, _p, _p, _c_int, _p]),

@@ -173,6 +173,47 @@ class LayerCache:
             torch.cuda.current_stream().cuda_stream), "kvq_attend")
         return out
 
+    # -- device-resident length (one captured CUDA graph serves a growing cache) ----------------------
+    def append_dyn(self, k_new, v_new, len_dev, slot_add=0):
+        """append() at slot `len_dev[0] + slot_add`, the length read on the device.  The host-side `len` is NOT
+        advanced: the caller owns the device counter (kvq_dec_counter_add) and re-syncs `len` when it leaves the graph."""
+        if not self.include_sparse:
+            raise NotImplementedError("dense-only native append: use QuantK/QuantV (legacy ops)")
+        s = torch.cuda.current_stream().cuda_stream
+        _lib.check(self.lib.kvq_append_kv_fused_dyn(
+            self.bits, self.H, self.Lmax, len_dev.data_ptr(), int(slot_add), self.n_each,
+            qc._f32(k_new, "k_new"), self.kcache.data_ptr(), self.klut.data_ptr(), self.klut_sub.data_ptr(),
+            self.thr_lower.data_ptr(), self.thr_upper.data_ptr(), self.k_outliers.data_ptr(),
+            self.k_outlier_idx.data_ptr(), qc._f32(v_new, "v_new"), self.vcache.data_ptr(), self.v_cent.data_ptr(),
+            self.v_cent_deq.data_ptr() if self.v_norm is not None else None, self.vlut.data_ptr(), self.vaff.data_ptr(),
+            self.v_outliers.data_ptr(), self.v_outlier_idx.data_ptr(), s), "kvq_append_kv_fused_dyn")
+
+    def attend_dyn(self, q, len_dev, len_add=0, rope_theta=10000.0, out=None, lse=None, L_cap=None):
+        """attend() over `min(len_dev[0] + len_add, L_cap)` slots, the length read on the device; grids, scratch and
+        the rope table are sized for L_cap (default: the whole allocation)."""
+        if not self.use_native_v:
+            raise NotImplementedError("device-resident length needs the native V form")
+        L_cap = self.Lmax if L_cap is None else int(L_cap)
+        need = self.lib.kvq_attend_scratch_bytes(self.H, max(L_cap, 1))
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(int(need) + 1024, dtype=torch.uint8, device=self.device)
+        pos_offset = self.n_sink + self.pos_base
+        rope, npos = qc.rope_table(self.device, rope_theta, L_cap + pos_offset + 1)
+        out = self._out if out is None else out
+        sp = self.include_sparse
+        ns = self.n_sink if self.sink_k is not None else 0
+        _lib.check(self.lib.kvq_attend_dyn(
+            self.bits, qc._f32(q, "q"), self.kcache.data_ptr(), self.klut_deq.data_ptr(),
+            self.k_outliers.data_ptr() if sp else None, self.k_outlier_idx.data_ptr() if sp else None,
+            self.vcache.data_ptr(), self.v_cent_deq.data_ptr(), self.vaff.data_ptr(),
+            self.v_outliers.data_ptr() if sp else None, self.v_outlier_idx.data_ptr() if sp else None,
+            self.n_out, self.H, self.Lmax, L_cap, len_dev.data_ptr(), int(len_add), rope.data_ptr(), npos,
+            float(rope_theta), pos_offset, self.sink_k.data_ptr() if ns else None,
+            self.sink_v.data_ptr() if ns else None, ns, out.data_ptr(),
+            lse.data_ptr() if lse is not None else None, self._scratch.data_ptr(),
+            torch.cuda.current_stream().cuda_stream), "kvq_attend_dyn")
+        return out
+
     def bytes_per_token(self):
         """Algorithmic HBM bytes one decode step reads per cached token (SURVEY.md 8d formula)."""
         b = 2 * self.H * HEAD_DIM * self.bits // 8 + 4 * 2 ** self.bits

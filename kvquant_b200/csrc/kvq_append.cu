@@ -274,13 +274,17 @@ __device__ void collect_selected(const uint32_t* keys, int n, int k, SelectSmem&
 
 template <int BITS>
 __global__ void __launch_bounds__(kFusedThreads, 1) append_kv_fused_kernel(
-    int hidden, int64_t Lmax, int64_t slot, int n_each,
+    int hidden, int64_t Lmax, int64_t slot, const int64_t* __restrict__ slot_dev, int n_each,
     const float* __restrict__ k_new, uint32_t* __restrict__ kcache, const float* __restrict__ klut,
     const float* __restrict__ klut_sub, const float* __restrict__ k_thr_lo, const float* __restrict__ k_thr_hi,
     float* __restrict__ k_out, int32_t* __restrict__ k_idx,
     const float* __restrict__ v_new, uint32_t* __restrict__ vcache, const float* __restrict__ v_cent,
     const float* __restrict__ v_cent_deq, float* __restrict__ vlut_tok, float* __restrict__ v_aff, float* __restrict__ v_out, int32_t* __restrict__ v_idx) {
   constexpr int N = Layout<BITS>::kLevels;
+  if (slot_dev != nullptr) {   // device-resident length (CUDA-graph replays with a growing cache): slot = *slot_dev + slot
+    slot += *slot_dev;
+    if (slot < 0 || slot >= Lmax) return;   // a full cache drops the token instead of writing out of bounds
+  }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_x = reinterpret_cast<float*>(smem_raw);                 // [hidden] raw values
   uint32_t* s_key = reinterpret_cast<uint32_t*>(s_x + hidden);     // [hidden] select keys
@@ -489,7 +493,7 @@ static int append_parallel(int bits, bool isv, int32_t* cache, const float* lut,
 }
 
 template <int BITS>
-static int launch_fused(int hidden, int64_t Lmax, int64_t slot, int n_each, const float* k_new, uint32_t* kcache,
+static int launch_fused(int hidden, int64_t Lmax, int64_t slot, const int64_t* slot_dev, int n_each, const float* k_new, uint32_t* kcache,
                         const float* klut, const float* klut_sub, const float* ktl, const float* kth, float* kout,
                         int32_t* kidx, const float* v_new, uint32_t* vcache, const float* vcent, const float* vcent_deq,
                         float* vlut, float* vaff, float* vout, int32_t* vidx, cudaStream_t st) {
@@ -500,7 +504,7 @@ static int launch_fused(int hidden, int64_t Lmax, int64_t slot, int n_each, cons
     if (e != cudaSuccess) return (int)e;
     attr_done[BITS] = true;
   }
-  append_kv_fused_kernel<BITS><<<2, kFusedThreads, smem, st>>>(hidden, Lmax, slot, n_each, k_new, kcache, klut,
+  append_kv_fused_kernel<BITS><<<2, kFusedThreads, smem, st>>>(hidden, Lmax, slot, slot_dev, n_each, k_new, kcache, klut,
                                                               klut_sub, ktl, kth, kout, kidx, v_new, vcache, vcent,
                                                               vcent_deq, vlut, vaff, vout, vidx);
   KVQ_LAUNCH_CHECK();
@@ -542,27 +546,51 @@ int kvq_append_v_sparse_parallel(int bits, int32_t* cache, const float* lut_tok,
   return append_parallel(bits, true, cache, lut_tok, newvec, nullptr, thr_lower, thr_upper, H, Lmax, T, stream);
 }
 
-int kvq_append_kv_fused(int bits, int H, int64_t Lmax, int64_t slot, int n_each, const float* k_new,
-                        int32_t* kcache, const float* klut, const float* klut_sub, const float* k_thr_lower,
-                        const float* k_thr_upper, float* k_outliers, int32_t* k_outlier_idx, const float* v_new,
-                        int32_t* vcache, const float* v_cent, const float* v_cent_deq, float* vlut_tok, float* v_aff,
-                        float* v_outliers, int32_t* v_outlier_idx, void* stream) {
+static int append_kv_fused_impl(int bits, int H, int64_t Lmax, int64_t slot, const int64_t* slot_dev, int n_each,
+                                const float* k_new, int32_t* kcache, const float* klut, const float* klut_sub,
+                                const float* k_thr_lower, const float* k_thr_upper, float* k_outliers,
+                                int32_t* k_outlier_idx, const float* v_new, int32_t* vcache, const float* v_cent,
+                                const float* v_cent_deq, float* vlut_tok, float* v_aff, float* v_outliers,
+                                int32_t* v_outlier_idx, void* stream) {
   if (!k_new || !kcache || !klut || !klut_sub || !k_thr_lower || !k_thr_upper || !k_outliers || !k_outlier_idx ||
       !v_new || !vcache || !v_cent || !vlut_tok || !v_outliers || !v_outlier_idx)
     return KVQ_E_NULL;
   const int hidden = H * kHeadDim;
-  if (H <= 0 || hidden > kMaxHidden || Lmax <= 0 || slot < 0 || slot >= Lmax) return KVQ_E_SHAPE;
+  if (H <= 0 || hidden > kMaxHidden || Lmax <= 0) return KVQ_E_SHAPE;
+  if (slot_dev == nullptr && (slot < 0 || slot >= Lmax)) return KVQ_E_SHAPE;
   if (n_each <= 0 || 2 * n_each > kMaxOut || 2 * (n_each + 1) > hidden) return KVQ_E_SHAPE;
   if ((reinterpret_cast<uintptr_t>(klut) & 15) != 0) return KVQ_E_ALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint32_t* kc = reinterpret_cast<uint32_t*>(kcache);
   uint32_t* vc = reinterpret_cast<uint32_t*>(vcache);
   switch (bits) {
-    case 4: return launch_fused<4>(hidden, Lmax, slot, n_each, k_new, kc, klut, klut_sub, k_thr_lower, k_thr_upper, k_outliers, k_outlier_idx, v_new, vc, v_cent, v_cent_deq, vlut_tok, v_aff, v_outliers, v_outlier_idx, st);
-    case 3: return launch_fused<3>(hidden, Lmax, slot, n_each, k_new, kc, klut, klut_sub, k_thr_lower, k_thr_upper, k_outliers, k_outlier_idx, v_new, vc, v_cent, v_cent_deq, vlut_tok, v_aff, v_outliers, v_outlier_idx, st);
-    case 2: return launch_fused<2>(hidden, Lmax, slot, n_each, k_new, kc, klut, klut_sub, k_thr_lower, k_thr_upper, k_outliers, k_outlier_idx, v_new, vc, v_cent, v_cent_deq, vlut_tok, v_aff, v_outliers, v_outlier_idx, st);
+    case 4: return launch_fused<4>(hidden, Lmax, slot, slot_dev, n_each, k_new, kc, klut, klut_sub, k_thr_lower, k_thr_upper, k_outliers, k_outlier_idx, v_new, vc, v_cent, v_cent_deq, vlut_tok, v_aff, v_outliers, v_outlier_idx, st);
+    case 3: return launch_fused<3>(hidden, Lmax, slot, slot_dev, n_each, k_new, kc, klut, klut_sub, k_thr_lower, k_thr_upper, k_outliers, k_outlier_idx, v_new, vc, v_cent, v_cent_deq, vlut_tok, v_aff, v_outliers, v_outlier_idx, st);
+    case 2: return launch_fused<2>(hidden, Lmax, slot, slot_dev, n_each, k_new, kc, klut, klut_sub, k_thr_lower, k_thr_upper, k_outliers, k_outlier_idx, v_new, vc, v_cent, v_cent_deq, vlut_tok, v_aff, v_outliers, v_outlier_idx, st);
     default: return KVQ_E_BITS;
   }
+}
+
+int kvq_append_kv_fused(int bits, int H, int64_t Lmax, int64_t slot, int n_each, const float* k_new,
+                        int32_t* kcache, const float* klut, const float* klut_sub, const float* k_thr_lower,
+                        const float* k_thr_upper, float* k_outliers, int32_t* k_outlier_idx, const float* v_new,
+                        int32_t* vcache, const float* v_cent, const float* v_cent_deq, float* vlut_tok, float* v_aff,
+                        float* v_outliers, int32_t* v_outlier_idx, void* stream) {
+  return append_kv_fused_impl(bits, H, Lmax, slot, nullptr, n_each, k_new, kcache, klut, klut_sub, k_thr_lower,
+                              k_thr_upper, k_outliers, k_outlier_idx, v_new, vcache, v_cent, v_cent_deq, vlut_tok,
+                              v_aff, v_outliers, v_outlier_idx, stream);
+}
+
+int kvq_append_kv_fused_dyn(int bits, int H, int64_t Lmax, const int64_t* len_dev, int64_t slot_add, int n_each,
+                            const float* k_new, int32_t* kcache, const float* klut, const float* klut_sub,
+                            const float* k_thr_lower, const float* k_thr_upper, float* k_outliers,
+                            int32_t* k_outlier_idx, const float* v_new, int32_t* vcache, const float* v_cent,
+                            const float* v_cent_deq, float* vlut_tok, float* v_aff, float* v_outliers,
+                            int32_t* v_outlier_idx, void* stream) {
+  if (!len_dev) return KVQ_E_NULL;
+  return append_kv_fused_impl(bits, H, Lmax, slot_add, len_dev, n_each, k_new, kcache, klut, klut_sub, k_thr_lower,
+                              k_thr_upper, k_outliers, k_outlier_idx, v_new, vcache, v_cent, v_cent_deq, vlut_tok,
+                              v_aff, v_outliers, v_outlier_idx, stream);
 }
 
 }  // extern "C"

@@ -29,9 +29,11 @@ __global__ void __launch_bounds__(1024) dec_rmsnorm_kernel(const __half* __restr
 
 // qkv fp16 [3*hidden] -> q (HF rotate-half RoPE at `pos`, modeling_llama.py:1851-1859) f32 [H,128], k f32, v f32
 __global__ void dec_rope_split_kernel(const __half* __restrict__ qkv, const float* __restrict__ inv_freq, float pos,
+                                      const int64_t* __restrict__ pos_dev,
                                       float* __restrict__ q, float* __restrict__ k, float* __restrict__ v, int hidden) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= hidden) return;
+  if (pos_dev != nullptr) pos += (float)(*pos_dev);   // device-resident position (graph replays with a growing cache)
   const int c = i & (kHeadDim - 1), j = c & (kHalf - 1);
   const float ang = inv_freq[j] * pos;
   float sn, cs;
@@ -51,6 +53,8 @@ __global__ void dec_silu_mul_kernel(const __half* __restrict__ gu, __half* __res
   const __half s = __float2half(g / (1.f + __expf(-g)));
   act[i] = __hmul(s, gu[n + i]);
 }
+
+__global__ void dec_counter_add_kernel(int64_t* c, int64_t d) { *c += d; }
 
 __global__ void dec_f32_to_f16_kernel(const float* __restrict__ a, __half* __restrict__ b, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -77,7 +81,24 @@ int kvq_dec_rope_split(const void* qkv_f16, const float* inv_freq, float pos, fl
   if (!qkv_f16 || !inv_freq || !q || !k || !v) return KVQ_E_NULL;
   if (hidden <= 0 || (hidden % kHeadDim) != 0) return KVQ_E_SHAPE;
   dec_rope_split_kernel<<<(hidden + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(qkv_f16), inv_freq, pos, q, k, v, hidden);
+      static_cast<const __half*>(qkv_f16), inv_freq, pos, nullptr, q, k, v, hidden);
+  KVQ_LAUNCH_CHECK();
+  return 0;
+}
+
+int kvq_dec_rope_split_dyn(const void* qkv_f16, const float* inv_freq, const int64_t* pos_dev, int64_t pos_add,
+                           float* q, float* k, float* v, int hidden, void* stream) {
+  if (!qkv_f16 || !inv_freq || !pos_dev || !q || !k || !v) return KVQ_E_NULL;
+  if (hidden <= 0 || (hidden % kHeadDim) != 0) return KVQ_E_SHAPE;
+  dec_rope_split_kernel<<<(hidden + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(qkv_f16), inv_freq, (float)pos_add, pos_dev, q, k, v, hidden);
+  KVQ_LAUNCH_CHECK();
+  return 0;
+}
+
+int kvq_dec_counter_add(int64_t* counter, int64_t delta, void* stream) {
+  if (!counter) return KVQ_E_NULL;
+  dec_counter_add_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(counter, delta);
   KVQ_LAUNCH_CHECK();
   return 0;
 }

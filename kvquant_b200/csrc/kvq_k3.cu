@@ -57,8 +57,10 @@ __global__ void __launch_bounds__(K3Cfg::kThreads, 1) k_scores3_kernel(const KPa
   const uint32_t tab0 = smem_u32(s_tab);
 
   // this CTA's token range [t_begin, t_limit): p.range is a multiple of 32
-  const int64_t t_begin = (int64_t)blockIdx.x * p.range;
-  const int64_t t_limit = min(p.L, t_begin + p.range);
+  const int64_t L_eff = k_eff_len(p);
+  const int64_t range = k_eff_range(p, L_eff);
+  const int64_t t_begin = (int64_t)blockIdx.x * range;
+  const int64_t t_limit = min(L_eff, t_begin + range);
   if (t_begin >= t_limit) return;
   const uint32_t pitch = (uint32_t)p.Lmax * 4u;
   const unsigned char* cb0 = reinterpret_cast<const unsigned char*>(p.cache + (int64_t)h0 * W * p.Lmax);

@@ -140,8 +140,10 @@ __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const
   // the packed words of item i+PD are loaded into a rotating register buffer while item i computes, the rope
   // values of the next chunk likewise.  A warp whose 32 tokens lie past the range skips the (last) tile, so a
   // partial tile costs only its live warps.
-  const int64_t t_begin = (int64_t)blockIdx.x * p.range;
-  const int64_t t_limit = min(p.L, t_begin + p.range);   // tokens this CTA may touch
+  const int64_t L_eff = k_eff_len(p);
+  const int64_t range = k_eff_range(p, L_eff);
+  const int64_t t_begin = (int64_t)blockIdx.x * range;
+  const int64_t t_limit = min(L_eff, t_begin + range);   // tokens this CTA may touch
   if (t_begin >= t_limit) return;
   const uint32_t pitch = (uint32_t)p.Lmax * 4u;      // row pitch in bytes (host checks Lmax < 2^30)
   const unsigned char* cb0 = reinterpret_cast<const unsigned char*>(p.cache + (int64_t)h0 * W * p.Lmax);
@@ -544,8 +546,12 @@ constexpr int kOutPersThreads = 512;
 __global__ void __launch_bounds__(kOutPersThreads) k_outlier_pers_kernel(
     const float* __restrict__ q, const float* __restrict__ outliers, const int32_t* __restrict__ outlier_idx,
     float* __restrict__ out, int64_t out_stride, int64_t L, int H, int n_out, const float2* __restrict__ rope,
-    int64_t rope_npos, int pos_offset, float scale) {
+    int64_t rope_npos, int pos_offset, float scale, const int64_t* __restrict__ len_dev, int64_t len_add) {
   extern __shared__ float2 s_qq[];                       // [H*128] = (q[c], q[c^64])
+  if (len_dev != nullptr) {                              // device-resident length: L is the cap the grid was sized for
+    const int64_t l = *len_dev + len_add;
+    L = l < 0 ? 0 : (l < L ? l : L);
+  }
   const int tid = threadIdx.x, lane = tid & 31;
   for (int i = tid; i < H * kHeadDim; i += kOutPersThreads) s_qq[i] = make_float2(q[i], q[i ^ kHalf]);
   __syncthreads();
@@ -601,6 +607,7 @@ static int launch_k_outliers(const KParams& p, int zero_first, float scale, cuda
   const int64_t total = p.L * p.n_out;
   const size_t smem = (size_t)p.H * kHeadDim * sizeof(float2);
   if (k_out_impl_table() || smem > 100 * 1024 || total >= ((int64_t)1 << 31) || p.L >= ((int64_t)1 << 25)) {
+    if (p.len_dev != nullptr) return KVQ_E_UNSUPPORTED;   // the gather form takes its length from the host
     const unsigned grid = (unsigned)((total + kOutThreads - 1) / kOutThreads);
     k_outlier_kernel<<<grid, kOutThreads, 0, st>>>(p.q, p.outliers, p.outlier_idx, p.out, p.out_stride, p.L, p.H,
                                                    p.n_out, p.rope, p.rope_npos, p.pos_offset, scale);
@@ -620,7 +627,8 @@ static int launch_k_outliers(const KParams& p, int zero_first, float scale, cuda
   const int per_sm = smem > 56 * 1024 ? 2 : 4;
   const unsigned grid = (unsigned)(want < (int64_t)sms * per_sm ? want : (int64_t)sms * per_sm);
   k_outlier_pers_kernel<<<grid, kOutPersThreads, smem, st>>>(p.q, p.outliers, p.outlier_idx, p.out, p.out_stride, p.L,
-                                                             p.H, p.n_out, p.rope, p.rope_npos, p.pos_offset, scale);
+                                                             p.H, p.n_out, p.rope, p.rope_npos, p.pos_offset, scale,
+                                                             p.len_dev, p.len_add);
   KVQ_LAUNCH_CHECK();
   return 0;
 }
@@ -679,7 +687,7 @@ static int k_impl() {
 }
 
 int k_scores_dispatch(int bits, const KParams& p, cudaStream_t st) {
-  const int impl = k_impl();
+  const int impl = p.len_dev != nullptr ? 0 : k_impl();   // the A/B variants take their length from the host
   if (impl == 0 && bits == 3) return k_scores3_dispatch(p, st);
   if (impl == 2 && (bits == 4 || bits == 3)) return k_pair_dispatch(bits, p, st);
   if (impl == 3 && p.H <= kMaxConstHeads) {
@@ -701,8 +709,9 @@ int k_scores_dispatch(int bits, const KParams& p, cudaStream_t st) {
 int k_scores_fused(int bits, const float* q, const int32_t* cache, float* scores, int64_t score_stride,
                    const float* lut, const float* outliers, const int32_t* outlier_idx, int n_out, int H,
                    int64_t Lmax, int64_t L, const float* rope, int64_t rope_npos, float theta, int pos_offset,
-                   float* gmax, float scale, cudaStream_t st) {
+                   float* gmax, float scale, const int64_t* len_dev, int64_t len_add, cudaStream_t st) {
   KParams p{};
+  p.len_dev = len_dev; p.len_add = len_add;
   p.q = q; p.cache = reinterpret_cast<const uint32_t*>(cache); p.out = scores; p.lut = lut;
   p.outliers = outliers; p.outlier_idx = outlier_idx; p.rope = reinterpret_cast<const float2*>(rope);
   p.gmax = gmax; p.Lmax = Lmax; p.L = L; p.out_stride = score_stride; p.rope_npos = rope_npos;

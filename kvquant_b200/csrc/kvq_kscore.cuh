@@ -15,6 +15,8 @@ struct KParams {
   float* gmax;               // [H] or null (fused mode: running max of scaled scores)
   int64_t Lmax, L, out_stride, rope_npos;
   int64_t range;             // tokens per CTA (multiple of 32), set by the launcher
+  const int64_t* len_dev;    // device-resident length (optional): L = min(*len_dev + len_add, L); L is then a cap
+  int64_t len_add;
   int H, n_out, pos_offset, tiles_per_cta;
   float theta;               // rope base (outlier scatter evaluates cos/sin of theta_j * pos directly)
   float scale;               // applied before the store (fused mode: 1/sqrt(128)); 1 for legacy
@@ -39,6 +41,18 @@ __device__ __forceinline__ void ffma2(float2& acc, const float2 a, const float2 
   asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%0,%1};"
       " fma.rn.f32x2 rc, ra, rb, rc; mov.b64 {%0,%1}, rc; }"
       : "+f"(acc.x), "+f"(acc.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+}
+// effective length / per-CTA range of a launch whose length lives on the device (CUDA-graph replays with a growing
+// cache): the grid was sized for the cap p.L, the kernel re-derives its split from the current length
+__device__ __forceinline__ int64_t k_eff_len(const KParams& p) {
+  if (p.len_dev == nullptr) return p.L;
+  const int64_t l = *p.len_dev + p.len_add;
+  return l < 0 ? 0 : (l < p.L ? l : p.L);
+}
+__device__ __forceinline__ int64_t k_eff_range(const KParams& p, int64_t L) {
+  if (p.len_dev == nullptr) return p.range;
+  const int64_t r = (L + gridDim.x - 1) / gridDim.x;
+  return (r + 31) & ~(int64_t)31;
 }
 // tokens per CTA when L tokens are cut into at most `splits` ranges: warp granularity, >= 32
 inline int64_t k_token_range(int64_t L, int64_t splits) {

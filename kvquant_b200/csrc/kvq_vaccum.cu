@@ -507,12 +507,12 @@ struct KParams;  // kvq_kscore.cu
 int k_scores_fused(int bits, const float* q, const int32_t* cache, float* scores, int64_t score_stride,
                    const float* lut, const float* outliers, const int32_t* outlier_idx, int n_out, int H,
                    int64_t Lmax, int64_t L, const float* rope, int64_t rope_npos, float theta, int pos_offset,
-                   float* gmax, float scale, cudaStream_t st);
+                   float* gmax, float scale, const int64_t* len_dev, int64_t len_add, cudaStream_t st);
 
 int v_native_dispatch(int bits, const float* score, int64_t score_stride, const float* gmax, const int32_t* cache,
                       const float* v_cent, const float* v_aff, const float* outliers, const int32_t* outlier_idx,
                       int n_out, int H, int64_t Lmax, int64_t L, float* out_o, float* out_l, int* n_cta,
-                      cudaStream_t st);
+                      const int64_t* len_dev, int64_t len_add, cudaStream_t st);
 
 static int check_v_common(int H, int64_t Lmax, int64_t L, const void* cache) {
   if (H <= 0 || (H & 3) != 0 || H > 64 || L < 0 || L > Lmax) return KVQ_E_SHAPE;
@@ -559,11 +559,13 @@ int64_t kvq_attend_scratch_bytes(int H, int64_t L) {
   return 4 * ((int64_t)H * round_up(L, 32) + H + (int64_t)H * 64 + (int64_t)kMaxPart * H * kHeadDim + (int64_t)kMaxPart * H) + 256;
 }
 
-int kvq_attend(int bits, const float* q, const int32_t* kcache, const float* klut, const float* k_outliers,
+}  // extern "C"
+
+static int attend_impl(int bits, const float* q, const int32_t* kcache, const float* klut, const float* k_outliers,
                const int32_t* k_outlier_idx, const int32_t* vcache, const float* vlut_tok, const float* v_cent,
                const float* v_aff, const float* v_outliers, const int32_t* v_outlier_idx, int n_out, int H, int64_t Lmax, int64_t L, const float* rope_cos_sin,
                int64_t rope_npos, float theta, int pos_offset, const void* sink_k, const void* sink_v, int n_sink,
-               float* out, float* out_lse, void* scratch, void* stream) {
+               float* out, float* out_lse, void* scratch, const int64_t* len_dev, int64_t len_add, void* stream) {
   if (!q || !kcache || !klut || !vcache || !rope_cos_sin || !out || !scratch) return KVQ_E_NULL;
   const bool native_v = (v_cent != nullptr && v_aff != nullptr);
   if (!native_v && !vlut_tok) return KVQ_E_NULL;
@@ -587,14 +589,14 @@ int kvq_attend(int bits, const float* q, const int32_t* kcache, const float* klu
   int n_cta = 0;
   if (L > 0) {
     rc = k_scores_fused(bits, q, kcache, scores, stride, klut, k_outliers, k_outlier_idx, n_out, H, Lmax, L,
-                        rope_cos_sin, rope_npos, theta, pos_offset, gmax, scale, st);
+                        rope_cos_sin, rope_npos, theta, pos_offset, gmax, scale, len_dev, len_add, st);
     if (rc) return rc;
     rc = KVQ_E_UNSUPPORTED;
     if (native_v)
       rc = v_native_dispatch(bits, scores, stride, gmax, vcache, v_cent, v_aff, v_outliers, v_outlier_idx, n_out, H,
-                             Lmax, L, part_o, part_l, &n_cta, st);
+                             Lmax, L, part_o, part_l, &n_cta, len_dev, len_add, st);
     // shapes whose native tile does not fit shared memory (e.g. 13B at 4 bits) fall back to the per-token-LUT kernel
-    if (rc == KVQ_E_UNSUPPORTED && vlut_tok != nullptr) {
+    if (rc == KVQ_E_UNSUPPORTED && vlut_tok != nullptr && len_dev == nullptr) {
       VParams p{};
       p.score = scores; p.lut_tok = vlut_tok; p.out = part_o; p.out_l = part_l; p.gmax = gmax;
       p.outliers = v_outliers; p.outlier_idx = v_outlier_idx;
@@ -607,6 +609,31 @@ int kvq_attend(int bits, const float* q, const int32_t* kcache, const float* klu
                                                 static_cast<const __half*>(sink_v), n_sink, out, out_lse);
   KVQ_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" {
+
+int kvq_attend(int bits, const float* q, const int32_t* kcache, const float* klut, const float* k_outliers,
+               const int32_t* k_outlier_idx, const int32_t* vcache, const float* vlut_tok, const float* v_cent,
+               const float* v_aff, const float* v_outliers, const int32_t* v_outlier_idx, int n_out, int H, int64_t Lmax, int64_t L, const float* rope_cos_sin,
+               int64_t rope_npos, float theta, int pos_offset, const void* sink_k, const void* sink_v, int n_sink,
+               float* out, float* out_lse, void* scratch, void* stream) {
+  return attend_impl(bits, q, kcache, klut, k_outliers, k_outlier_idx, vcache, vlut_tok, v_cent, v_aff, v_outliers,
+                     v_outlier_idx, n_out, H, Lmax, L, rope_cos_sin, rope_npos, theta, pos_offset, sink_k, sink_v, n_sink,
+                     out, out_lse, scratch, nullptr, 0, stream);
+}
+
+int kvq_attend_dyn(int bits, const float* q, const int32_t* kcache, const float* klut, const float* k_outliers,
+                   const int32_t* k_outlier_idx, const int32_t* vcache, const float* v_cent, const float* v_aff,
+                   const float* v_outliers, const int32_t* v_outlier_idx, int n_out, int H, int64_t Lmax, int64_t L_cap,
+                   const int64_t* len_dev, int64_t len_add, const float* rope_cos_sin, int64_t rope_npos, float theta,
+                   int pos_offset, const void* sink_k, const void* sink_v, int n_sink, float* out, float* out_lse,
+                   void* scratch, void* stream) {
+  if (!len_dev || !v_cent || !v_aff) return KVQ_E_NULL;
+  if (L_cap <= 0) return KVQ_E_SHAPE;
+  return attend_impl(bits, q, kcache, klut, k_outliers, k_outlier_idx, vcache, nullptr, v_cent, v_aff, v_outliers,
+                     v_outlier_idx, n_out, H, Lmax, L_cap, rope_cos_sin, rope_npos, theta, pos_offset, sink_k, sink_v,
+                     n_sink, out, out_lse, scratch, len_dev, len_add, stream);
 }
 
 int kvq_attend_merge(const float* parts, int n_parts, int H, float* out, void* stream) {

@@ -34,6 +34,8 @@ struct VNParams {
   const float* outliers;     // [>=L, n_out] or null
   const int32_t* outlier_idx;
   int64_t Lmax, L, score_stride;
+  const int64_t* len_dev;    // device-resident length (optional): L = min(*len_dev + len_add, L); L is then a cap
+  int64_t len_add;
   int H, n_out, tiles_per_cta, n_stages, box_rows;
 };
 
@@ -199,9 +201,13 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
     prefetch_tensormap(&tmap);
   }
 
-  const int64_t n_tiles_total = (p.L + kNT - 1) / kNT;
-  const int64_t tile0 = (int64_t)blockIdx.x * p.tiles_per_cta;
-  const int ntiles = (int)max((int64_t)0, min((int64_t)p.tiles_per_cta, n_tiles_total - tile0));
+  // device-resident length: the grid was sized for the cap p.L; CTAs past the current length write zero partials
+  int64_t L_eff = p.L;
+  if (p.len_dev != nullptr) { const int64_t l = *p.len_dev + p.len_add; L_eff = l < 0 ? 0 : (l < p.L ? l : p.L); }
+  const int64_t n_tiles_total = (L_eff + kNT - 1) / kNT;
+  const int64_t tiles_per_cta = p.len_dev != nullptr ? (n_tiles_total + gridDim.x - 1) / gridDim.x : p.tiles_per_cta;
+  const int64_t tile0 = (int64_t)blockIdx.x * tiles_per_cta;
+  const int ntiles = (int)max((int64_t)0, min(tiles_per_cta, n_tiles_total - tile0));
   const int nbox = rows / p.box_rows;
 
   auto issue_tile = [&](int it) {  // thread 0 only
@@ -229,7 +235,7 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
       w_s[i] = -INFINITY; w_m[i] = 0.f; w_a[i] = make_float2(0.f, 0.f);
       if (e < n_w) {
         const int h = e >> 5, tl = e & 31;
-        if (t0 + tl < p.L) {
+        if (t0 + tl < L_eff) {
           w_s[i] = p.score[(int64_t)h * p.score_stride + t0 + tl];
           w_m[i] = p.gmax[h];
           w_a[i] = *reinterpret_cast<const float2*>(p.v_aff + 2 * (t0 + tl));
@@ -271,7 +277,7 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int k = lane + 32 * r;
-        const bool in = (t < p.L) && (k < p.n_out);
+        const bool in = (t < L_eff) && (k < p.n_out);
         opre_v[2 * j + r] = in ? p.outliers[t * p.n_out + k] : 0.f;
         opre_i[2 * j + r] = in ? p.outlier_idx[t * p.n_out + k] : 0;
       }
@@ -325,7 +331,7 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
         }
         for (int k = lane + 64; k < p.n_out; k += 32) {   // n_out > 64: unprefetched tail
           const int64_t t = (tile0 + it) * kNT + tl;
-          if (t < p.L) {
+          if (t < L_eff) {
             const float v = p.outliers[t * p.n_out + k];
             const int idx = p.outlier_idx[t * p.n_out + k];
             if (v != 0.f) red_add_f32(obase + idx, v * wbuf[(idx >> 7) * kNT + tl]);
@@ -410,8 +416,9 @@ static int launch_vn(VNParams p, const int32_t* cache, int* n_cta_out, cudaStrea
 int v_native_dispatch(int bits, const float* score, int64_t score_stride, const float* gmax, const int32_t* cache,
                       const float* v_cent, const float* v_aff, const float* outliers, const int32_t* outlier_idx,
                       int n_out, int H, int64_t Lmax, int64_t L, float* out_o, float* out_l, int* n_cta,
-                      cudaStream_t st) {
+                      const int64_t* len_dev, int64_t len_add, cudaStream_t st) {
   VNParams p{};
+  p.len_dev = len_dev; p.len_add = len_add;
   p.score = score; p.gmax = gmax; p.v_cent = v_cent; p.v_aff = v_aff; p.out_o = out_o; p.out_l = out_l;
   p.outliers = outliers; p.outlier_idx = outlier_idx; p.Lmax = Lmax; p.L = L; p.score_stride = score_stride;
   p.H = H; p.n_out = n_out;

@@ -97,6 +97,7 @@ class DecoderStage:
         self.device = torch.device(device)
         self.sp = sp
         self.global_pos = None   # sp: absolute position of the new token (set by the driver)
+        self.dyn = None          # device-resident length / position counters (enable_device_length)
         gen = torch.Generator(device=self.device)
         gen.manual_seed(seed * 1000 + lo)
         self.layers = [DecoderLayer(cfg, self.device, gen, quantizer, with_sinks=(sp is None or sp[0] == 0))
@@ -171,22 +172,39 @@ class DecoderStage:
         flip = 0
         for ly in self.layers:
             c = ly.cache
-            # absolute position of the new token
-            pos = self.global_pos if self.sp is not None else c.n_sink + c.pos_base + c.len
+            dyn = self.dyn          # device-resident length / position (one graph for a growing cache) or None
             self._gemv(ly.wqkv, x, 3, b["qkv"], norm_w=ly.n1)
-            _lib.check(lib.kvq_dec_rope_split(b["qkv"].data_ptr(), self.inv_freq.data_ptr(), float(pos),
-                                              b["q"].data_ptr(), b["k"].data_ptr(), b["v"].data_ptr(), hid, st))
+            if dyn is None:
+                # absolute position of the new token
+                pos = self.global_pos if self.sp is not None else c.n_sink + c.pos_base + c.len
+                _lib.check(lib.kvq_dec_rope_split(b["qkv"].data_ptr(), self.inv_freq.data_ptr(), float(pos),
+                                                  b["q"].data_ptr(), b["k"].data_ptr(), b["v"].data_ptr(), hid, st))
+            else:
+                _lib.check(lib.kvq_dec_rope_split_dyn(b["qkv"].data_ptr(), self.inv_freq.data_ptr(),
+                                                      dyn["pos"].data_ptr(), 0, b["q"].data_ptr(), b["k"].data_ptr(),
+                                                      b["v"].data_ptr(), hid, st))
+            qh = b["q"].view(H, HEAD_DIM)
             if self.sp is None:
-                c.append(b["k"], b["v"])                 # pre-RoPE K, per-token V: quantise + outlier split
-                o = c.attend(b["q"].view(H, HEAD_DIM), rope_theta=cfg.rope_theta)   # f32 [H,128]
+                if dyn is None:
+                    c.append(b["k"], b["v"])             # pre-RoPE K, per-token V: quantise + outlier split
+                    o = c.attend(qh, rope_theta=cfg.rope_theta)   # f32 [H,128]
+                else:
+                    c.append_dyn(b["k"], b["v"], dyn["len"])
+                    o = c.attend_dyn(qh, dyn["len"], 1, rope_theta=cfg.rope_theta)
             else:
                 import torch.distributed as dist
                 rank, world = self.sp
-                if rank == world - 1:
-                    c.append(b["k"], b["v"])             # the newest token lives on the last shard
                 part = b["part"]
-                c.attend(b["q"].view(H, HEAD_DIM), rope_theta=cfg.rope_theta, out=part[:hid].view(H, HEAD_DIM),
-                         lse=part[hid:])
+                owner = rank == world - 1                # the newest token lives on the last shard
+                if dyn is None:
+                    if owner:
+                        c.append(b["k"], b["v"])
+                    c.attend(qh, rope_theta=cfg.rope_theta, out=part[:hid].view(H, HEAD_DIM), lse=part[hid:])
+                else:
+                    if owner:
+                        c.append_dyn(b["k"], b["v"], dyn["len"])
+                    c.attend_dyn(qh, dyn["len"], 1 if owner else 0, rope_theta=cfg.rope_theta,
+                                 out=part[:hid].view(H, HEAD_DIM), lse=part[hid:])
                 dist.all_gather_into_tensor(b["gath"], part)      # H*129 floats per rank over NVLink
                 o = b["om"]
                 _lib.check(lib.kvq_attend_merge(b["gath"].data_ptr(), world, H, o.data_ptr(), st))
@@ -195,7 +213,24 @@ class DecoderStage:
             self._gemv(ly.wgu, x, 3, b["gu"], norm_w=ly.n2)
             x = self._gemv(ly.wdown, b["gu"], 2, xs[flip], residual=x)
             flip ^= 1
+        if self.dyn is not None:                          # advance the device counters inside the step
+            if self.sp is None or self.sp[0] == self.sp[1] - 1:
+                _lib.check(lib.kvq_dec_counter_add(self.dyn["len"].data_ptr(), 1, st))
+            if self.dyn["pos"].data_ptr() != self.dyn["len"].data_ptr():
+                _lib.check(lib.kvq_dec_counter_add(self.dyn["pos"].data_ptr(), 1, st))
         return x
+
+    def enable_device_length(self, L, pos):
+        """Switch the stage to the device-resident length: every layer cache holds L tokens, the next token sits at
+        absolute position `pos`.  Returns the counters (int64[1] each; the same tensor when pos tracks len)."""
+        ln = torch.full((1,), int(L), dtype=torch.int64, device=self.device)
+        ps = torch.full((1,), int(pos), dtype=torch.int64, device=self.device)
+        self.dyn = dict(len=ln, pos=ps)
+        return self.dyn
+
+    def set_device_length(self, L, pos):
+        self.dyn["len"].fill_(int(L))
+        self.dyn["pos"].fill_(int(pos))
 
     def forward_torch(self, x):
         """Same dataflow with plain torch element-wise ops (reference for the helper kernels; used by tests)."""
@@ -228,20 +263,31 @@ class DecoderStage:
 
 class GraphedStage:
     """One decode step of a stage captured in a CUDA graph (the reference's host syncs make that impossible;
-    here nothing in the step touches the host).  The captured step appends at slot L and attends over L+1 slots;
-    replaying it re-runs exactly that step (the fused append overwrites its slot, so replays are idempotent)."""
+    here nothing in the step touches the host).
 
-    def __init__(self, stage: DecoderStage, L: int, first: bool, last_to_logits: bool):
+    dynamic=False: the captured step appends at slot L and attends over L+1 slots; replaying it re-runs exactly that
+    step (the fused append overwrites its slot, so replays are idempotent).
+    dynamic=True : the cache length and the token position live in device memory and are advanced inside the step, so
+    every replay of the SAME graph is the next decode step of a growing cache (slot L, L+1, ...)."""
+
+    def __init__(self, stage: DecoderStage, L: int, first: bool, last_to_logits: bool, dynamic: bool = False,
+                 pos: int = None):
         self.stage = stage
         dev = stage.device
         cfg = stage.cfg
         self.tok = torch.zeros(1, dtype=torch.long, device=dev)
         self.x_in = torch.zeros(cfg.hidden, dtype=torch.float16, device=dev)
         self.first, self.last_to_logits = first, last_to_logits
+        self.dynamic, self.L0, self.steps = dynamic, L, 0
+        c0 = stage.layers[0].cache
+        self.pos0 = (c0.n_sink + c0.pos_base + L) if pos is None else pos
+        if dynamic:
+            stage.enable_device_length(L, self.pos0)
 
         def body():
             x = stage.embed_token(self.tok) if first else self.x_in
-            stage.set_len(L)
+            if not dynamic:
+                stage.set_len(L)
             y = stage.forward(x)
             return y
 
@@ -263,10 +309,20 @@ class GraphedStage:
             self.y = body()
             if last_to_logits and stage.with_head:
                 self.logits = stage.head(self.y)
-        stage.set_len(L + 1)
+        if dynamic:
+            # the eager warm-up steps advanced the counters (and wrote slots >= L that later steps overwrite)
+            stage.set_device_length(L, self.pos0)
+            stage.set_len(L)
+        else:
+            stage.set_len(L + 1)
 
     def replay(self):
         self.graph.replay()
+        if self.dynamic:
+            self.steps += 1
+            sp = self.stage.sp
+            if sp is None or sp[0] == sp[1] - 1:       # host mirror of the device counter (on the rank that appends)
+                self.stage.set_len(self.L0 + self.steps)
 
 
 def layer_step_bytes(cfg: DecodeConfig, L: int):

@@ -351,3 +351,42 @@ def test_sequence_shard_merge_equals_single_attend():
     out = torch.empty((H, 128), device=DEV)
     _lib.check(_lib.load().kvq_attend_merge(parts.data_ptr(), 2, H, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
     assert rel_err(out.cpu().numpy(), want.cpu().numpy())[0] < 1e-5
+
+
+@pytest.mark.parametrize("bits,L,n_sink", [(4, 900, 0), (3, 611, 3), (2, 200, 0)])
+def test_device_resident_length_equals_host_length(bits, L, n_sink):
+    """kvq_attend_dyn / kvq_append_kv_fused_dyn (length read from device memory, grids sized for the whole
+    allocation) give the results of the host-length entry points: same attend output for several lengths with ONE
+    set of launch parameters, and the same cache words / outlier rows for an append."""
+    from kvquant_b200.cache import LayerCache
+    c, k, v = oracle_cache(bits, L)
+    klut, vcent = quantizer(bits)
+    sp = spec()
+    a = LayerCache.from_luts(bits, 32, c.Lmax, klut, vcent, device=DEV, n_sink=n_sink)
+    a.load_state(c)
+    b = LayerCache.from_luts(bits, 32, c.Lmax, klut, vcent, device=DEV, n_sink=n_sink)
+    b.load_state(c)
+    if n_sink:
+        ks = torch.randn((32, 128, n_sink), device=DEV).half()
+        vs = torch.randn((32, n_sink, 128), device=DEV).half()
+        a.set_sinks(ks, vs)
+        b.set_sinks(ks, vs)
+    len_dev = torch.zeros(1, dtype=torch.int64, device=DEV)
+    for Lt in (L, L // 2 + 3, 33, 1):
+        q = cu(O.rope_rotate_q(sp.q_vec(3 + Lt), Lt + n_sink, 10000.0))
+        a.len = Lt
+        want = a.attend(q).clone()
+        len_dev.fill_(Lt - 1)
+        got = b.attend_dyn(q, len_dev, 1).clone()
+        assert rel_err(got.cpu().numpy(), want.cpu().numpy())[0] < 1e-5, Lt
+    # append at the device-resident slot == append at the host slot
+    a.len = L
+    kn, vn = cu(sp.k_tokens(1, 501)[0]), cu(sp.v_tokens(1, 502)[0])
+    a.append(kn, vn)
+    len_dev.fill_(L)
+    b.append_dyn(kn, vn, len_dev)
+    torch.cuda.synchronize()
+    for name in ("kcache", "vcache", "k_outlier_idx", "v_outlier_idx", "k_outliers", "v_outliers", "vlut", "vaff"):
+        ta, tb = getattr(a, name), getattr(b, name)
+        sl = (slice(None), slice(None), L) if name.endswith("cache") else (L,)
+        assert torch.equal(ta[sl], tb[sl]), name
