@@ -16,8 +16,6 @@ namespace kvq {
 
 constexpr int kGemvThreads = 512;
 constexpr int kGemvMaxK = 14336;
-constexpr int kGemvMaxSeg = 4;      // K segments per row pair (small N only)
-constexpr int kGemvMaxPairs = 32;   // row pairs per CTA when K is segmented
 
 __device__ __forceinline__ uint4 ld_w16(const uint4* p, uint64_t pol) {
   uint4 v;
@@ -41,21 +39,14 @@ __device__ __forceinline__ int xperm(int i) {
   return (i & ~255) | ((i & 4) << 5) | ((i & 0xF8) >> 1) | (i & 3);
 }
 
-__device__ __forceinline__ void gemv_store(void* y, int y_f32, const __half* residual, int r, float v) {
-  if (residual != nullptr) v += __half2float(residual[r]);
-  if (y_f32) static_cast<float*>(y)[r] = v;
-  else static_cast<__half*>(y)[r] = __float2half(v);
-}
-
 // XK: 0 = fp16 vector, 1 = f32 vector, 2 = fp16 [2K] gate|up -> silu(gate)*up, 3 = fp16 vector + RMSNorm(norm_w)
 template <int XK>
 __global__ void __launch_bounds__(kGemvThreads, 1) dec_gemv_kernel(
     const uint4* __restrict__ W, int N, int K, const void* __restrict__ x, const __half* __restrict__ norm_w, float eps,
-    const __half* __restrict__ residual, void* __restrict__ y, int y_f32, int nseg) {
+    const __half* __restrict__ residual, void* __restrict__ y, int y_f32) {
   extern __shared__ float4 s_x4[];                  // f(x) as f32 [K]
   float* s_x = reinterpret_cast<float*>(s_x4);
   __shared__ float s_red[32];
-  __shared__ float s_part[kGemvMaxPairs * kGemvMaxSeg * 2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if constexpr (XK == 0) {
@@ -91,27 +82,20 @@ __global__ void __launch_bounds__(kGemvThreads, 1) dec_gemv_kernel(
   }
   __syncthreads();
 
-  // this CTA's rows: equal contiguous blocks.  Work item = (row pair, K segment): with few rows per CTA (N = 4096:
-  // 27-28) whole-row items would leave warps idle and a single warp walking 43 chunks in sequence, so K is cut into
-  // nseg segments whose partial sums meet in shared memory.
+  // this CTA's rows: equal contiguous blocks
   const int r_begin = (int)(((int64_t)N * blockIdx.x) / gridDim.x);
   const int r_end = (int)(((int64_t)N * (blockIdx.x + 1)) / gridDim.x);
   const uint64_t pol = policy_evict_first();
   const int kc = K >> 8;                            // 16-byte chunks per lane per row (K % 256 == 0)
   const int row_u4 = K >> 3;                        // uint4 per row
   constexpr int NW = kGemvThreads / 32;
-  const int npairs = (r_end - r_begin + 1) >> 1;
-  const int nitems = npairs * nseg;
-  for (int item = warp; item < nitems; item += NW) {
-    const int pair = item / nseg, seg = item - pair * nseg;
-    const int r = r_begin + 2 * pair;
+  for (int r = r_begin + 2 * warp; r < r_end; r += 2 * NW) {
     const bool two = (r + 1) < r_end;
     const uint4* w0 = W + (int64_t)r * row_u4 + lane;
     const uint4* w1 = two ? w0 + row_u4 : w0;
     float a0 = 0.f, a1 = 0.f;
-    int c = (kc * seg) / nseg;
-    const int c_end = (kc * (seg + 1)) / nseg;
-    for (; c + 4 <= c_end; c += 4) {
+    int c = 0;
+    for (; c + 4 <= kc; c += 4) {
       uint4 u0[4], u1[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { u0[i] = ld_w16(w0 + (c + i) * 32, pol); u1[i] = ld_w16(w1 + (c + i) * 32, pol); }
@@ -122,7 +106,7 @@ __global__ void __launch_bounds__(kGemvThreads, 1) dec_gemv_kernel(
         a1 = dot8(u1[i], xa, xb, a1);
       }
     }
-    for (; c < c_end; ++c) {
+    for (; c < kc; ++c) {
       const uint4 u0 = ld_w16(w0 + c * 32, pol), u1 = ld_w16(w1 + c * 32, pol);
       const float4 xa = s_x4[c * 64 + lane], xb = s_x4[c * 64 + 32 + lane];
       a0 = dot8(u0, xa, xb, a0);
@@ -130,18 +114,12 @@ __global__ void __launch_bounds__(kGemvThreads, 1) dec_gemv_kernel(
     }
     a0 = warp_sum(a0);
     a1 = warp_sum(a1);
-    if (nseg == 1) {
-      if (lane < 2 && (lane == 0 || two)) gemv_store(y, y_f32, residual, r + lane, lane ? a1 : a0);
-    } else if (lane < 2) {
-      s_part[(pair * kGemvMaxSeg + seg) * 2 + lane] = lane ? a1 : a0;
-    }
-  }
-  if (nseg > 1) {
-    __syncthreads();
-    for (int i = tid; i < r_end - r_begin; i += kGemvThreads) {
-      float v = 0.f;
-      for (int sgi = 0; sgi < nseg; ++sgi) v += s_part[((i >> 1) * kGemvMaxSeg + sgi) * 2 + (i & 1)];
-      gemv_store(y, y_f32, residual, r_begin + i, v);
+    if (lane < 2 && (lane == 0 || two)) {
+      const int rr = r + lane;
+      float v = lane ? a1 : a0;
+      if (residual != nullptr) v += __half2float(residual[rr]);
+      if (y_f32) static_cast<float*>(y)[rr] = v;
+      else static_cast<__half*>(y)[rr] = __float2half(v);
     }
   }
 }
@@ -176,21 +154,15 @@ int kvq_dec_gemv(const void* w_f16, int N, int K, const void* x, int x_kind, con
   const int sms = num_sms_cached();
   const int grid = N < sms ? N : sms;
   const size_t smem = (size_t)K * 4;
-  const int rows_per_cta = (N + grid - 1) / grid;
-  int nseg = 1;
-  if (rows_per_cta <= 2 * kGemvMaxPairs) {          // few rows per CTA: cut K so that every warp has work
-    nseg = rows_per_cta <= 32 ? 4 : 2;
-    while (nseg > 1 && (K >> 8) / nseg < 4) nseg >>= 1;
-  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uint4* W = static_cast<const uint4*>(w_f16);
   const __half* nw = static_cast<const __half*>(norm_w_f16);
   const __half* res = static_cast<const __half*>(residual_f16);
   switch (x_kind) {
-    case 0: dec_gemv_kernel<0><<<grid, kGemvThreads, smem, st>>>(W, N, K, x, nw, eps, res, y, y_f32, nseg); break;
-    case 1: dec_gemv_kernel<1><<<grid, kGemvThreads, smem, st>>>(W, N, K, x, nw, eps, res, y, y_f32, nseg); break;
-    case 2: dec_gemv_kernel<2><<<grid, kGemvThreads, smem, st>>>(W, N, K, x, nw, eps, res, y, y_f32, nseg); break;
-    default: dec_gemv_kernel<3><<<grid, kGemvThreads, smem, st>>>(W, N, K, x, nw, eps, res, y, y_f32, nseg); break;
+    case 0: dec_gemv_kernel<0><<<grid, kGemvThreads, smem, st>>>(W, N, K, x, nw, eps, res, y, y_f32); break;
+    case 1: dec_gemv_kernel<1><<<grid, kGemvThreads, smem, st>>>(W, N, K, x, nw, eps, res, y, y_f32); break;
+    case 2: dec_gemv_kernel<2><<<grid, kGemvThreads, smem, st>>>(W, N, K, x, nw, eps, res, y, y_f32); break;
+    default: dec_gemv_kernel<3><<<grid, kGemvThreads, smem, st>>>(W, N, K, x, nw, eps, res, y, y_f32); break;
   }
   KVQ_LAUNCH_CHECK();
   return 0;

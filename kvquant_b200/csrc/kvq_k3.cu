@@ -148,6 +148,12 @@ __global__ void __launch_bounds__(K3Cfg::kThreads, 1) k_scores3_kernel(const KPa
         old[hl] = 0.f;
         if (p.accumulate && live && (FULL || hl < nh)) old[hl] = p.out[(int64_t)(h0 + hl) * p.out_stride + t];
       }
+      if (p.opart != nullptr && live) {   // outlier partials of this token's 8 heads: two 16-byte loads (rows are padded)
+        const float4* src = reinterpret_cast<const float4*>(p.opart + t * p.opart_stride + h0);
+        const float4 a = __ldcg(src), b = __ldcg(src + 1);
+        old[0] += a.x; old[1] += a.y; old[2] += a.z; old[3] += a.w;
+        old[4] += b.x; old[5] += b.y; old[6] += b.z; old[7] += b.w;
+      }
 #pragma unroll
       for (int hl = 0; hl < G; ++hl) {
         if (FULL || hl < nh) {

@@ -218,6 +218,14 @@ __global__ void __launch_bounds__(KCfg<BITS>::kThreads, 1) k_scores_kernel(const
       old[hl] = 0.f;
       if (p.accumulate && live && hl < nh) old[hl] = p.out[(int64_t)(h0 + hl) * p.out_stride + t];
     }
+    if (p.opart != nullptr && live) {   // outlier partials of this token's G heads: G/4 16-byte loads (rows are padded)
+      const float4* src = reinterpret_cast<const float4*>(p.opart + t * p.opart_stride + h0);
+#pragma unroll
+      for (int i = 0; i < G / 4; ++i) {
+        const float4 v = __ldcg(src + i);
+        old[4 * i] += v.x; old[4 * i + 1] += v.y; old[4 * i + 2] += v.z; old[4 * i + 3] += v.w;
+      }
+    }
 #pragma unroll
     for (int hl = 0; hl < G; ++hl) {
       if (hl < nh) {
@@ -538,15 +546,20 @@ __global__ void __launch_bounds__(kOutThreads) k_outlier_kernel(
 // Persistent form (default).  ncu on the kernel above: load/store data path 75 % busy -- per ENTRY one scattered
 // 8-byte rope read plus TWO scattered reads of q.  Here CTAs are persistent and keep (q[c], q[c^64]) for all channels
 // in shared memory (one 8-byte shared read per entry instead of two scattered global ones); the rope values still
-// come from the table.  Measured alternatives: evaluating cosf/sinf(theta_j * pos) per entry
+// come from the table.  In the fused path the sums go to a TOKEN-major partial buffer (a token's heads share one
+// 128-byte line, so a warp's ~25 reductions coalesce into one or two L1 requests: 46 -> 38 us at 128K).
+// Measured alternatives: a second, token-major copy of the rope table read with coalesced
+// row loads + shuffles instead of the gather (59 us: it loads rows for the zero-valued pads too and adds 8 shuffles
+// per entry); evaluating cosf/sinf(theta_j * pos) per entry
 // instead of the gather (50 us vs 55 us at 128K, 40 M instead of 26 M warp instructions), and accumulating into a
 // per-CTA [H][256-token] shared tile with coalesced write-out instead of global atomics (85-98 us: shared-memory
 // fp32 atomics are compare-and-swap loops).
 constexpr int kOutPersThreads = 512;
 __global__ void __launch_bounds__(kOutPersThreads) k_outlier_pers_kernel(
     const float* __restrict__ q, const float* __restrict__ outliers, const int32_t* __restrict__ outlier_idx,
-    float* __restrict__ out, int64_t out_stride, int64_t L, int H, int n_out, const float2* __restrict__ rope,
-    int64_t rope_npos, int pos_offset, float scale, const int64_t* __restrict__ len_dev, int64_t len_add) {
+    float* __restrict__ out, int64_t stride_h, int64_t stride_t, int64_t L, int H, int n_out,
+    const float2* __restrict__ rope, int64_t rope_npos, int pos_offset, float scale,
+    const int64_t* __restrict__ len_dev, int64_t len_add) {
   extern __shared__ float2 s_qq[];                       // [H*128] = (q[c], q[c^64])
   if (len_dev != nullptr) {                              // device-resident length: L is the cap the grid was sized for
     const int64_t l = *len_dev + len_add;
@@ -588,7 +601,7 @@ __global__ void __launch_bounds__(kOutPersThreads) k_outlier_pers_kernel(
     }
     const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
     const bool leader = (lane == 0) || (kprev != key);
-    if (leader && e < total && contrib != 0.f) atomicAdd(out + (int64_t)h * out_stride + t, contrib);
+    if (leader && e < total && contrib != 0.f) atomicAdd(out + (int64_t)h * stride_h + (int64_t)t * stride_t, contrib);
   }
 }
 
@@ -601,13 +614,15 @@ static int k_out_impl_table() {   // KVQ_KOUT_IMPL=table selects the non-persist
 // zero_first = 1: `out` is a fresh score buffer (fused path) and is cleared before the scatter
 static int launch_k_outliers(const KParams& p, int zero_first, float scale, cudaStream_t st) {
   if (zero_first) {
-    cudaError_t e = cudaMemsetAsync(p.out, 0, sizeof(float) * (size_t)p.H * (size_t)p.out_stride, st);
+    cudaError_t e = p.opart != nullptr
+        ? cudaMemsetAsync(const_cast<float*>(p.opart), 0, sizeof(float) * (size_t)p.L * (size_t)p.opart_stride, st)
+        : cudaMemsetAsync(p.out, 0, sizeof(float) * (size_t)p.H * (size_t)p.out_stride, st);
     if (e != cudaSuccess) return (int)e;
   }
   const int64_t total = p.L * p.n_out;
   const size_t smem = (size_t)p.H * kHeadDim * sizeof(float2);
   if (k_out_impl_table() || smem > 100 * 1024 || total >= ((int64_t)1 << 31) || p.L >= ((int64_t)1 << 25)) {
-    if (p.len_dev != nullptr) return KVQ_E_UNSUPPORTED;   // the gather form takes its length from the host
+    if (p.len_dev != nullptr || p.opart != nullptr) return KVQ_E_UNSUPPORTED;   // host length, head-major target only
     const unsigned grid = (unsigned)((total + kOutThreads - 1) / kOutThreads);
     k_outlier_kernel<<<grid, kOutThreads, 0, st>>>(p.q, p.outliers, p.outlier_idx, p.out, p.out_stride, p.L, p.H,
                                                    p.n_out, p.rope, p.rope_npos, p.pos_offset, scale);
@@ -626,7 +641,11 @@ static int launch_k_outliers(const KParams& p, int zero_first, float scale, cuda
   const int64_t want = (total + kOutPersThreads - 1) / kOutPersThreads;
   const int per_sm = smem > 56 * 1024 ? 2 : 4;
   const unsigned grid = (unsigned)(want < (int64_t)sms * per_sm ? want : (int64_t)sms * per_sm);
-  k_outlier_pers_kernel<<<grid, kOutPersThreads, smem, st>>>(p.q, p.outliers, p.outlier_idx, p.out, p.out_stride, p.L,
+  // token-major target (fused path): a token's heads share one 128-byte line, so a warp's ~25 reductions (one or
+  // two tokens) coalesce into one or two L1 requests instead of one per head row
+  float* dst = p.opart != nullptr ? const_cast<float*>(p.opart) : p.out;
+  const int64_t sh = p.opart != nullptr ? 1 : p.out_stride, stt = p.opart != nullptr ? p.opart_stride : 1;
+  k_outlier_pers_kernel<<<grid, kOutPersThreads, smem, st>>>(p.q, p.outliers, p.outlier_idx, dst, sh, stt, p.L,
                                                              p.H, p.n_out, p.rope, p.rope_npos, p.pos_offset, scale,
                                                              p.len_dev, p.len_add);
   KVQ_LAUNCH_CHECK();
@@ -709,7 +728,8 @@ int k_scores_dispatch(int bits, const KParams& p, cudaStream_t st) {
 int k_scores_fused(int bits, const float* q, const int32_t* cache, float* scores, int64_t score_stride,
                    const float* lut, const float* outliers, const int32_t* outlier_idx, int n_out, int H,
                    int64_t Lmax, int64_t L, const float* rope, int64_t rope_npos, float theta, int pos_offset,
-                   float* gmax, float scale, const int64_t* len_dev, int64_t len_add, cudaStream_t st) {
+                   float* gmax, float scale, const int64_t* len_dev, int64_t len_add, float* opart, int opart_stride,
+                   cudaStream_t st) {
   KParams p{};
   p.len_dev = len_dev; p.len_add = len_add;
   p.q = q; p.cache = reinterpret_cast<const uint32_t*>(cache); p.out = scores; p.lut = lut;
@@ -717,10 +737,13 @@ int k_scores_fused(int bits, const float* q, const int32_t* cache, float* scores
   p.gmax = gmax; p.Lmax = Lmax; p.L = L; p.out_stride = score_stride; p.rope_npos = rope_npos;
   p.H = H; p.n_out = n_out; p.pos_offset = pos_offset; p.scale = scale; p.accumulate = 0; p.theta = theta;
   if (outliers != nullptr) {
-    // outlier contributions are deposited UNSCALED (the dense kernel applies `scale` to out + S)
+    // outlier contributions are deposited UNSCALED (the dense kernel applies `scale` to partial + S), token-major
+    // when the caller provides the partial buffer (and the variant in use supports it)
+    const bool tm = opart != nullptr && !k_out_impl_table() && k_impl() == 0;
+    if (tm) { p.opart = opart; p.opart_stride = opart_stride; }
     const int rc = launch_k_outliers(p, /*zero_first=*/1, 1.f, st);
     if (rc != 0) return rc;
-    p.accumulate = 1;
+    if (!tm) p.accumulate = 1;
   }
   return k_scores_dispatch(bits, p, st);
 }

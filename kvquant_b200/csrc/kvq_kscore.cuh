@@ -21,6 +21,8 @@ struct KParams {
   float theta;               // rope base (outlier scatter evaluates cos/sin of theta_j * pos directly)
   float scale;               // applied before the store (fused mode: 1/sqrt(128)); 1 for legacy
   int accumulate;            // 1: out = (out + S)*scale, 0: out = S*scale
+  const float* opart;        // fused path: outlier partial sums, TOKEN-major [L][opart_stride] (null: none / in `out`)
+  int opart_stride;          // floats per token row (H rounded up to 32: one 128-byte line per 32 heads)
 };
 
 // compile-time loop (immediate LDS offsets and PRMT selectors need constant expressions)

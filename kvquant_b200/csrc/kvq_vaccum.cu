@@ -507,7 +507,8 @@ struct KParams;  // kvq_kscore.cu
 int k_scores_fused(int bits, const float* q, const int32_t* cache, float* scores, int64_t score_stride,
                    const float* lut, const float* outliers, const int32_t* outlier_idx, int n_out, int H,
                    int64_t Lmax, int64_t L, const float* rope, int64_t rope_npos, float theta, int pos_offset,
-                   float* gmax, float scale, const int64_t* len_dev, int64_t len_add, cudaStream_t st);
+                   float* gmax, float scale, const int64_t* len_dev, int64_t len_add, float* opart, int opart_stride,
+                   cudaStream_t st);
 
 int v_native_dispatch(int bits, const float* score, int64_t score_stride, const float* gmax, const int32_t* cache,
                       const float* v_cent, const float* v_aff, const float* outliers, const int32_t* outlier_idx,
@@ -556,7 +557,10 @@ static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 static const int kMaxPart = 256;
 
 int64_t kvq_attend_scratch_bytes(int H, int64_t L) {
-  return 4 * ((int64_t)H * round_up(L, 32) + H + (int64_t)H * 64 + (int64_t)kMaxPart * H * kHeadDim + (int64_t)kMaxPart * H) + 256;
+  // scores [H][L'] + gmax [H] + sink scores [H][64] + partial o / l of <= kMaxPart CTAs + token-major K-outlier
+  // partials [L'][H'] (H' = H rounded up to 32)
+  return 4 * ((int64_t)H * round_up(L, 32) + H + (int64_t)H * 64 + (int64_t)kMaxPart * H * kHeadDim + (int64_t)kMaxPart * H +
+              round_up(L, 32) * round_up(H, 32)) + 256;
 }
 
 }  // extern "C"
@@ -583,13 +587,15 @@ static int attend_impl(int bits, const float* q, const int32_t* kcache, const fl
   float* sink_scores = gmax + H;
   float* part_o = sink_scores + (int64_t)H * 64;
   float* part_l = part_o + (int64_t)kMaxPart * H * kHeadDim;
+  float* opart = part_l + (int64_t)kMaxPart * H;          // 16-byte aligned: every block above is a multiple of 4 floats
+  const int opart_stride = (int)round_up(H, 32);
   const float scale = 0.08838834764831845f;  // 1/sqrt(128)  (modeling_llama.py:1959,1973)
   attend_init_kernel<<<H, kHeadDim, 0, st>>>(q, static_cast<const __half*>(sink_k), n_sink, sink_scores, gmax, scale);
   KVQ_LAUNCH_CHECK();
   int n_cta = 0;
   if (L > 0) {
     rc = k_scores_fused(bits, q, kcache, scores, stride, klut, k_outliers, k_outlier_idx, n_out, H, Lmax, L,
-                        rope_cos_sin, rope_npos, theta, pos_offset, gmax, scale, len_dev, len_add, st);
+                        rope_cos_sin, rope_npos, theta, pos_offset, gmax, scale, len_dev, len_add, opart, opart_stride, st);
     if (rc) return rc;
     rc = KVQ_E_UNSUPPORTED;
     if (native_v)
