@@ -95,7 +95,8 @@ KVQ_API int kvq_rope_table_build(float* rope_cos_sin, float theta, int64_t n_pos
  *   p = t + pos_offset.   q f32 [B,H,128]; mul f32 [B,H,L]; lut f32 [H*128,2^bits];
  *   outliers f32 [>=L, n_out], outlier_idx i32 [>=L, n_out] (flat channel index), B must be 1 when given;
  *   rope: table from kvq_rope_table_build(theta) covering positions [0, pos_offset+L), with row length rope_npos
- *   (used by the dense kernel); theta: the same rope base, used by the outlier pre-pass (42 sincos per token).
+ *   (used by the dense kernel and by the outlier scatter); theta: the rope base the table was built with (kept in the
+ *   signature for callers that build the table lazily; the kernels take every cos/sin from the table).
  * kvq_v_matvec replaces ..._transposed_mha_batched_fused_opt (quant_cuda.cpp:214-224; kernel 3211-3433) and ..._opt2
  * (quant_cuda.cpp:226-238; + SPMV_ATOMIC_BALANCED 436-470):
  *   mul[b,h,c] += sum_t (LUT[t,code] (+) outlier) * score[b,h,t].   score f32 [B,H,L]; mul f32 [B,H,128].

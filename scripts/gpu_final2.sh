@@ -14,5 +14,5 @@ timeout 900 python bench.py --steps 20 --warmup 3 --workload 7b-4b-128k --no-cpu
 timeout 900 python bench.py --steps 20 --warmup 3 --workload 7b-4b-32k --no-cpu-baseline > gpurun_out/bench_4b32k.log 2> gpurun_out/bench_4b32k.err; echo "bench32k rc=$?"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.log 2> gpurun_out/bench_reference.err; echo "bench ref rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_scores|v_native|k_outlier|attend_|append_kv|dec_' -c 1400 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1; echo "ncu list rc=$?"
-PROBE_QUICK=1 PROBE_BITS=3,4 PROBE_L=131072 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_scores|v_native|k_outlier|attend_' -c 60 -o gpurun_out/prof_attend python scripts/gpu_probe.py > gpurun_out/ncu_full.log 2>&1
+PROBE_QUICK=1 PROBE_BITS=3,4 PROBE_L=131072 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_scores|v_native|k_outlier|attend_' -c 28 -o gpurun_out/prof_attend python scripts/gpu_probe.py > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out | tail -25
