@@ -205,6 +205,9 @@ def main():
     par = args.parallelism
     if par == "auto":
         par = "sp" if (world > 1 and L % world == 0) else "pp"
+    par_label = ("sp%d" if (par == "sp" and world > 1) else "pp%d") % world
+    if args.impl == "reference":
+        par = "pp"          # the CPU arm runs the whole job (all L tokens, all layers) on rank 0's host cores
     sp_mode = (par == "sp" and world > 1)
     if sp_mode and L % world:
         raise SystemExit("sp needs seq_len divisible by the number of GPUs")
@@ -214,7 +217,7 @@ def main():
     cfg = kd.DecodeConfig.llama7b(bits=bits, n_sink=n_sink, max_len=L_local + headroom)
     sp, quantizer = build_quantizer(bits, cfg.n_heads, dev)
     config = {"workload": args.workload, "description": desc, "bits": bits, "seq_len": L + n_sink, "n_sink": n_sink,
-              "outliers": "1% (21+21 per token per cache)", "layers": cfg.n_layers, "parallelism": ("sp%d" if sp_mode else "pp%d") % world,
+              "outliers": "1% (21+21 per token per cache)", "layers": cfg.n_layers, "parallelism": par_label,
               "l2_policy": "inputs larger than L2: every step streams all layers' caches (>= 4 GB) and 13.5 GB of weights",
               "step": ("one CUDA-graph replay = the next decode step of a growing cache (length and position live in "
                        "device memory; step i appends slot L+i and attends over L+i+1 slots)") if args.graph == "dynamic"
