@@ -452,6 +452,25 @@ def attend_ideal(scores_kernel_f64, v_fn, head_dim=HEAD_DIM, sink_scores=None):
 # --------------------------------------------------------------------------------------------------
 # a whole quantised cache built token by token with the reference decode semantics
 # --------------------------------------------------------------------------------------------------
+def attend_partial(scores_kernel_f64, v_fn, head_dim=HEAD_DIM):
+    """Partial attention over one contiguous token shard (sequence-sharded decode): the shard's own
+    softmax-normalised output and the log-sum-exp of its scaled scores.  float64: (out [H,128], lse [H])."""
+    s = np.asarray(scores_kernel_f64, dtype=np.float64) / np.sqrt(head_dim)
+    m = s.max(axis=-1, keepdims=True)
+    e = np.exp(s - m)
+    l = e.sum(axis=-1, keepdims=True)
+    return v_fn(e / l), (m + np.log(l))[:, 0]
+
+
+def merge_partials(outs, lses):
+    """Exact merge of per-shard (out, lse) pairs: out = sum_r exp(lse_r - M) out_r / sum_r exp(lse_r - M), M = max lse
+    (what kvq_attend_merge computes on the device).  outs [R,H,128], lses [R,H] -> [H,128] float64."""
+    outs = np.asarray(outs, dtype=np.float64)
+    lses = np.asarray(lses, dtype=np.float64)
+    w = np.exp(lses - lses.max(axis=0, keepdims=True))          # [R,H]
+    return (w[:, :, None] * outs).sum(axis=0) / w.sum(axis=0)[:, None]
+
+
 class OracleCache:
     """QuantK + QuantV state for one layer, filled token by token exactly as
     QuantK/QuantV.forward_fused_sparse do (ML.py:653-751, 1069-1176)."""
