@@ -122,6 +122,7 @@ def cpu_baseline_run(layer_arrays, bits, H, Lmax, L, n_out, n_layers, theta, pos
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import build_oracle_c
     lib = build_oracle_c.load()
+    lib.kvq_port_set_threads(len(os.sched_getaffinity(0)))   # not OMP_NUM_THREADS (torchrun sets it to 1)
     cores = lib.kvq_port_threads()
     a = layer_arrays
     q = np.ascontiguousarray(a["q"], dtype=np.float32)

@@ -24,6 +24,8 @@ def load():
     lib = ctypes.CDLL(build())
     P, I, L64, F = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
     lib.kvq_port_threads.restype = I
+    lib.kvq_port_set_threads.argtypes = [I]
+    lib.kvq_port_set_threads.restype = None
     lib.kvq_port_k_scores.argtypes = [I, P, P, P, P, P, I, I, L64, L64, F, I, P]
     lib.kvq_port_v_out.argtypes = [I, P, P, P, P, P, I, I, L64, L64, P]
     lib.kvq_port_attend.argtypes = [I, P, P, P, P, P, P, P, P, P, I, I, L64, L64, F, I, P, P]

@@ -31,6 +31,15 @@ static inline uint32_t code_of(const uint32_t* w, int64_t stride, int bits, int 
   }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline is to use every host core it may run on */
+void kvq_port_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int kvq_port_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
