@@ -498,11 +498,12 @@ static int launch_fused(int hidden, int64_t Lmax, int64_t slot, const int64_t* s
                         int32_t* kidx, const float* v_new, uint32_t* vcache, const float* vcent, const float* vcent_deq,
                         float* vlut, float* vaff, float* vout, int32_t* vidx, cudaStream_t st) {
   const size_t smem = (size_t)hidden * (4 + 4 + 1);
-  static bool attr_done[5] = {false, false, false, false, false};
-  if (!attr_done[BITS]) {
+  static PerDeviceOnce attr_once;   // (one instance per BITS instantiation)
+  bool& attr_done = attr_once.cur();
+  if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(append_kv_fused_kernel<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_done[BITS] = true;
+    attr_done = true;
   }
   append_kv_fused_kernel<BITS><<<2, kFusedThreads, smem, st>>>(hidden, Lmax, slot, slot_dev, n_each, k_new, kcache, klut,
                                                               klut_sub, ktl, kth, kout, kidx, v_new, vcache, vcent,

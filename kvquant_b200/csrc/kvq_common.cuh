@@ -26,6 +26,18 @@ extern unsigned long long g_launch_count;  // host-side counter (kvq_launch_coun
     if (e__ != cudaSuccess) return (int)e__;       \
   } while (0)
 
+// "done once per device" flag for cudaFuncSetAttribute & co.  Function attributes are per device, and the reference
+// drives several GPUs from ONE process (LlamaModel.set_devices, modeling_llama.py:2428-2453), so a plain static bool
+// would leave every device but the first without its shared-memory opt-in.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool& cur() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return done[d & 63];
+  }
+};
+
 template <int BITS> struct Layout {
   static constexpr int kWords = kHeadDim * BITS / 32;  // int32 rows per head: 16 / 12 / 8
   static constexpr int kLevels = 1 << BITS;            // LUT entries

@@ -141,7 +141,8 @@ int kvq_dec_gemv(const void* w_f16, int N, int K, const void* x, int x_kind, con
   if (x == y || residual_f16 == x) { /* in-place on the residual is fine; the input vector must not be the output */
     if (x == y) return KVQ_E_SHAPE;
   }
-  static bool attr_done = false;
+  static PerDeviceOnce attr_once;
+  bool& attr_done = attr_once.cur();
   if (!attr_done) {
     const int mx = kGemvMaxK * 4;
     cudaError_t e = cudaFuncSetAttribute(dec_gemv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);

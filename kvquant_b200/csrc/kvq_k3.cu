@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(K3Cfg::kThreads, 1) k_scores3_kernel(const KPa
 
 int k_scores3_dispatch(const KParams& p, cudaStream_t st) {
   using C = K3Cfg;
-  static bool attr_done = false;
+  static PerDeviceOnce attr_once;
+  bool& attr_done = attr_once.cur();
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(k_scores3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem);
     if (e != cudaSuccess) return (int)e;

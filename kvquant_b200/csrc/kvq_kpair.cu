@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(PCfg<BITS>::kThreads, 1) k_pair_kernel(const K
 template <int BITS>
 static int launch_k_pair(const KParams& p, cudaStream_t st) {
   using C = PCfg<BITS>;
-  static bool attr_done = false;
+  static PerDeviceOnce attr_once;
+  bool& attr_done = attr_once.cur();
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(k_pair_kernel<BITS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem);
     if (e != cudaSuccess) return (int)e;

@@ -474,7 +474,8 @@ template <int BITS>
 static int launch_k_kappa(const KParams& p, cudaStream_t st) {
   using C = KKCfg<BITS>;
   const size_t smem = 256 + (size_t)C::G * kHeadDim * C::CS + (size_t)C::D * C::NRW * C::TT * 4;
-  static bool attr_done = false;
+  static PerDeviceOnce attr_once;
+  bool& attr_done = attr_once.cur();
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(k_scores_kappa_kernel<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -629,7 +630,11 @@ static int launch_k_outliers(const KParams& p, int zero_first, float scale, cuda
     KVQ_LAUNCH_CHECK();
     return 0;
   }
-  static size_t smem_set = 48 * 1024;
+  static size_t smem_set_dev[64];   // per device: largest dynamic shared memory opted in so far (0 = default 48 KiB)
+  int dev_idx = 0;
+  cudaGetDevice(&dev_idx);
+  size_t& smem_set = smem_set_dev[dev_idx & 63];
+  if (smem_set == 0) smem_set = 48 * 1024;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(k_outlier_pers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -670,7 +675,8 @@ template <int BITS>
 static int launch_k_scores(const KParams& p, cudaStream_t st) {
   using C = KCfg<BITS>;
   const size_t smem = 256 + (size_t)C::G * kHeadDim * C::N * sizeof(float2) + (size_t)C::G * kHeadDim * 4;
-  static bool attr_done = false;
+  static PerDeviceOnce attr_once;
+  bool& attr_done = attr_once.cur();
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(k_scores_kernel<BITS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

@@ -447,17 +447,18 @@ int make_cache_tensor_map(CUtensorMap* out, const void* base, uint64_t rows, uin
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
-static int g_sms = 0;
+static int g_sms[64];   // per device (one process may drive several GPUs, see PerDeviceOnce)
 int num_sms_cached();
 static int num_sms() { return num_sms_cached(); }
 int num_sms_cached() {
-  if (!g_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sms <= 0) g_sms = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = g_sms[dev & 63];
+  if (!n) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
   }
-  return g_sms;
+  return n;
 }
 
 constexpr uint32_t kSmemBudget = 227u * 1024u;
@@ -475,7 +476,8 @@ static int launch_v(VParams p, const int32_t* cache, int* n_cta_out, cudaStream_
   }
   if (S < 2) return KVQ_E_UNSUPPORTED;
   p.n_stages = S;
-  static bool attr_done = false;
+  static PerDeviceOnce attr_once;
+  bool& attr_done = attr_once.cur();
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(v_accum_kernel<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
     if (e != cudaSuccess) return (int)e;

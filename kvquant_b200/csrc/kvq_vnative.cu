@@ -391,7 +391,8 @@ static int launch_vn(VNParams p, const int32_t* cache, int* n_cta_out, cudaStrea
   }
   if (S < 2) return KVQ_E_UNSUPPORTED;
   p.n_stages = S;
-  static bool attr_done = false;
+  static PerDeviceOnce attr_once;
+  bool& attr_done = attr_once.cur();
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(v_native_kernel<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVNSmemBudget);
     if (e != cudaSuccess) return (int)e;
