@@ -47,6 +47,20 @@ def build_k_lookup_table(upper, lower, centroids, num_heads, normscale=None, nor
     return out
 
 
+def _on_cache_device(fn):
+    """Run a LayerCache method with the cache's device current (the C ABI launches on the current device; one
+    process may hold caches on several GPUs, as the reference's set_devices mode does)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *a, **kw)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **kw)
+    return wrapped
+
+
 class LayerCache:
     """Native quantised K+V cache of one layer (reference-compatible tensor layouts)."""
 
@@ -58,6 +72,8 @@ class LayerCache:
             raise ValueError("max_len must be a multiple of 4 (TMA row pitch)")
         self.hidden = self.H * HEAD_DIM
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.include_sparse = include_sparse
         self.n_each = n_outliers_each(self.hidden, sparsity_threshold)
         self.n_out = 2 * self.n_each
@@ -132,6 +148,7 @@ class LayerCache:
         self.vaff[:, 0] = sf
         self.vaff[:, 1] = self.vlut[:, 0] - c0 * sf
 
+    @_on_cache_device
     def append(self, k_new, v_new):
         """Quantise + pack + outlier split of one token's K and V, entirely on the device (one launch)."""
         if not self.include_sparse:
@@ -148,6 +165,7 @@ class LayerCache:
             "kvq_append_kv_fused")
         self.len += 1
 
+    @_on_cache_device
     def attend(self, q, rope_theta=10000.0, out=None, lse=None):
         """softmax(q.K^T/sqrt(128)).V over sinks + quantised slots.  q: f32 [H,128] already rotated at its own
         position.  Returns f32 [H,128].  lse (optional f32 [H]) receives the log-sum-exp of the scaled scores, which
@@ -174,6 +192,7 @@ class LayerCache:
         return out
 
     # -- device-resident length (one captured CUDA graph serves a growing cache) ----------------------
+    @_on_cache_device
     def append_dyn(self, k_new, v_new, len_dev, slot_add=0):
         """append() at slot `len_dev[0] + slot_add`, the length read on the device.  The host-side `len` is NOT
         advanced: the caller owns the device counter (kvq_dec_counter_add) and re-syncs `len` when it leaves the graph."""
@@ -188,6 +207,7 @@ class LayerCache:
             self.v_cent_deq.data_ptr() if self.v_norm is not None else None, self.vlut.data_ptr(), self.vaff.data_ptr(),
             self.v_outliers.data_ptr(), self.v_outlier_idx.data_ptr(), s), "kvq_append_kv_fused_dyn")
 
+    @_on_cache_device
     def attend_dyn(self, q, len_dev, len_add=0, rope_theta=10000.0, out=None, lse=None, L_cap=None):
         """attend() over `min(len_dev[0] + len_add, L_cap)` slots, the length read on the device; grids, scratch and
         the rope table are sized for L_cap (default: the whole allocation)."""
