@@ -3,6 +3,7 @@ symbol include/kvquant_b200.h declares; the Python surface has exactly the refer
 import ctypes
 import os
 import re
+import pytest
 
 from _util import ROOT
 
@@ -70,3 +71,25 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("oracle/_ref", ""), os.path.join(dirpath, f)
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/kvquant_b200.h is a C header (no C++ or torch types): it compiles as C99 and as C++11, and a C program
+    that only includes it links against libkvquant_b200.so and runs without a GPU (the cgo / JNI / ctypes view)."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi_c.c"
+    src.write_text('#include "kvquant_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%d %s\\n", kvq_abi_version(), kvq_error_string(KVQ_E_SHAPE)); return 0; }\n')
+    inc = os.path.join(root, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
+    subprocess.check_call(["g++", "-std=c++11", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)])
+    lib = os.path.join(root, "kvquant_b200", "libkvquant_b200.so")
+    if not os.path.exists(lib) or shutil.which("gcc") is None:
+        pytest.skip("library not built")
+    exe = tmp_path / "abi_c"
+    subprocess.check_call(["gcc", "-std=c99", "-I", inc, str(src), lib, "-o", str(exe),
+                           "-Wl,-rpath," + os.path.dirname(lib), "-Wl,-rpath,/usr/local/cuda/lib64"])
+    out = subprocess.check_output([str(exe)], text=True).split(None, 1)
+    assert out[0] == "1" and out[1].strip()
