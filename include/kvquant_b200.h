@@ -90,7 +90,7 @@ KVQ_API int kvq_rope_table_build(float* rope_cos_sin, float theta, int64_t n_pos
  *
  * kvq_k_matvec replaces vecquant{4,3,2}matmul_nuq_perchannel_transposed_rope_mha_batched_fused_opt
  * (quant_cuda.cpp:188-198; kernel 3040-3209) and, with outliers != NULL, ..._opt2 (quant_cuda.cpp:200-212; dense
- * kernel + SPMV_ATOMIC_ROPE_BALANCED 472-521) in ONE launch:
+ * kernel + SPMV_ATOMIC_ROPE_BALANCED 472-521) in ONE call (outlier scatter + dense kernel on `stream`):
  *   mul[b,h,t] += sum_c (LUT[h,c,code] (+) outlier) * (cos(th_c*p)*q[b,h,c] + s_c*sin(th_c*p)*q[b,h,(c+64)%128])
  *   p = t + pos_offset.   q f32 [B,H,128]; mul f32 [B,H,L]; lut f32 [H*128,2^bits];
  *   outliers f32 [>=L, n_out], outlier_idx i32 [>=L, n_out] (flat channel index), B must be 1 when given;

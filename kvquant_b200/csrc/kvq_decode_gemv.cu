@@ -138,9 +138,7 @@ int kvq_dec_gemv(const void* w_f16, int N, int K, const void* x, int x_kind, con
   if (N <= 0 || K <= 0 || (K & 255) != 0 || K > kGemvMaxK) return KVQ_E_SHAPE;
   if (x_kind < 0 || x_kind > 3 || (x_kind == 3 && !norm_w_f16)) return KVQ_E_SHAPE;
   if ((reinterpret_cast<uintptr_t>(w_f16) & 15) != 0) return KVQ_E_ALIGN;
-  if (x == y || residual_f16 == x) { /* in-place on the residual is fine; the input vector must not be the output */
-    if (x == y) return KVQ_E_SHAPE;
-  }
+  if (x == y) return KVQ_E_SHAPE;   // in place on the residual is fine; the input vector must not be the output
   static PerDeviceOnce attr_once;
   bool& attr_done = attr_once.cur();
   if (!attr_done) {
