@@ -382,6 +382,31 @@ def orig_k_token_outliers(k, thr_lower, thr_upper, zeropoint):
     return cols, vals
 
 
+def csr_grow(ptr, idx, val, start, new_idx, new_val, cachelen):
+    """Host side of vecquant4appendvec{K,V}sparseorig (DK.cu:765-823): append one token's `count` outliers to the
+    growing CSR (K: rows = tokens) / CSC (V: cols = tokens) arrays.  The SpMV is balanced at 10 nonzeros per thread;
+    `start[k]` = the token at which thread k's first nonzero was appended (new threads start at the current token).
+    Plain Python lists in, lists out: (ptr, idx, val, start, num_threads)."""
+    count = len(new_idx)
+    if len(ptr) == 0:                                   # DK.cu:768-786
+        ptr2 = [0, count]
+        idx2, val2 = list(new_idx), list(new_val)
+        nthreads = (count + 9) // 10
+        start2 = [int(cachelen)] * nthreads
+    else:                                               # DK.cu:788-820
+        ptr2 = list(ptr) + [len(idx) + count]
+        prevmax = len(start)
+        if count > 0:
+            idx2, val2 = list(idx) + list(new_idx), list(val) + list(new_val)
+            nthreads = (len(idx2) + 9) // 10
+            new_alloc = nthreads - prevmax
+            start2 = list(start) + [int(cachelen)] * new_alloc if new_alloc > 0 else list(start)
+        else:
+            idx2, val2, start2 = list(idx), list(val), list(start)
+            nthreads = (len(idx2) + 9) // 10
+    return ptr2, idx2, val2, start2, nthreads
+
+
 def csr_k_scores(q, rows_ptr_tokens, cols, vals, L, rope_theta, pos_offset, num_heads):
     """SPMV_ATOMIC_CSR_ROPE_BALANCED semantics (DK.cu:523-614), token-major CSR given as per-token
     (start,end) pointer array rows_ptr_tokens [L+1]."""

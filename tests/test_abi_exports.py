@@ -93,3 +93,40 @@ def test_header_is_plain_c_and_links_against_the_library(tmp_path):
                            "-Wl,-rpath," + os.path.dirname(lib), "-Wl,-rpath,/usr/local/cuda/lib64"])
     out = subprocess.check_output([str(exe)], text=True).split(None, 1)
     assert out[0] == "1" and out[1].strip()
+
+
+def test_csr_growth_glue_matches_the_oracle():
+    """quant_cuda._grow_csr (host glue of the uncapped 'orig' appends, quant_cuda_kernel.cu:765-823) on CPU tensors
+    against the oracle's restatement, token by token, including empty tokens and the 10-nonzeros-per-thread
+    start array."""
+    import numpy as np
+    import torch
+    from _util import O
+    from kvquant_b200 import quant_cuda as qc
+    g = np.random.default_rng(5)
+    e = torch.empty(0, dtype=torch.int32)
+    ptr, idx, val, start = e, e, torch.empty(0), e
+    optr, oidx, oval, ostart = [], [], [], []
+    for t in range(60):
+        count = int(g.choice([0, 0, 1, 3, 9, 10, 11, 25]))
+        ni = torch.tensor(np.sort(g.choice(4096, count, replace=False)), dtype=torch.int32)
+        nv = torch.tensor(g.normal(size=count), dtype=torch.float32)
+        ptr, idx, val, start, nthr = qc._grow_csr(ptr, idx, val, start, ni, nv, count, t, "cpu")
+        optr, oidx, oval, ostart, onthr = O.csr_grow(optr, oidx, oval, ostart, ni.tolist(), nv.tolist(), t)
+        assert nthr == onthr == (len(oidx) + 9) // 10
+        assert ptr.tolist() == optr and idx.tolist() == oidx and start.tolist() == ostart
+        assert np.array_equal(val.numpy(), np.asarray(oval, dtype=np.float32))
+    assert ptr.tolist()[-1] == len(oidx) and len(ptr) == 61
+
+
+def test_algorithmic_bytes_match_the_survey_figures():
+    """roofline.achieved is computed from SURVEY.md 8(d)'s per-token figures: 7B 4-bit+1% = 4832 B/token/layer,
+    3-bit+1% = 3776, 4-bit dense-only = 4160; outlier width 42 (7B) / 52 (13B)."""
+    from kvquant_b200 import decode as kd
+    from kvquant_b200.cache import n_outliers_each
+    assert kd.layer_step_bytes(kd.DecodeConfig.llama7b(bits=4), 1) == 4832
+    assert kd.layer_step_bytes(kd.DecodeConfig.llama7b(bits=3), 1) == 3776
+    cfg = kd.DecodeConfig.llama7b(bits=4)
+    cfg.include_sparse = False
+    assert kd.layer_step_bytes(cfg, 1) == 4160
+    assert 2 * n_outliers_each(4096, 0.99) == 42 and 2 * n_outliers_each(5120, 0.99) == 52
