@@ -10,11 +10,11 @@
 // at once: a byte (4-bit), a 6-bit field (3-bit) or a nibble (2-bit) of the packed word indexes a lane-private
 // table of float2 {cent[lo], cent[hi]} (lane-private = bank-conflict-free for any code pattern), and one packed
 // FFMA2 accumulates both channels:   1 address op + 1 LDS.64 + 1 FFMA2  per TWO elements.
-// What bounds this kernel is the shared-memory crossbar (one 8-byte lookup per 2 elements = 4 B/element), see
-// DESIGN.md section 5.
+// What bounds this kernel is the SM's load/store data path (one 8-byte lookup per 2 elements plus the outlier
+// reductions), see DESIGN.md sections 4.2 and 7.
 //
-// Data movement is the same as kvq_vaccum.cu: TMA (cp.async.bulk.tensor.2d, 64B swizzle) streams the
-// [H*W rows x 16 tokens] code slab of a tile into a 3-4 stage ring behind mbarriers; thread = packed word row.
+// Data movement: TMA (cp.async.bulk.tensor.2d, 128B swizzle, boxes of up to 256 rows) streams the
+// [H*W rows x 32 tokens] code slab of a tile into a 2-3 stage ring behind mbarriers; thread = packed word row.
 #include "kvq_common.cuh"
 #include <stdlib.h>
 
