@@ -1,5 +1,6 @@
-// kvquant_b200 -- Q.K^T decode matvec over the packed pre-RoPE key cache, RoPE and the fixed-width outlier
-// stream fused into one launch.
+// kvquant_b200 -- Q.K^T decode matvec over the packed pre-RoPE key cache with RoPE applied at read time: the dense
+// kernel (all widths; 3-bit has its own in kvq_k3.cu), the outlier scatter that runs in front of it, the rope table
+// builder, and the A/B variants kept behind KVQ_K_IMPL.
 //
 // Replaces (reference deployment/kvquant/quant_cuda_kernel.cu):
 //   VecQuant{4,3,2}MatMulKernelNUQPerChannelTransposedRopeMHABatchedFusedOpt   3040-3209, 3692-4115, 4747-4996
@@ -8,7 +9,7 @@
 //   S[h,t] = sum_c (LUT[h,c,code(h,c,t)] (+) outlier(h,c,t)) * (cos(th_j p) q[h,c] + s_c sin(th_j p) q[h,(c+64)%128])
 //   j = c % 64, p = t + pos_offset.
 //
-// Design (DESIGN.md section 4):
+// Design (DESIGN.md section 4.1):
 //   * The reference evaluates powf+cosf+sinf per (head, channel, token): 4096 sincos per token per layer make it
 //     ALU-bound.  cos/sin depend on (j, p) only, so they come from a table rope[j][p] built ONCE with the
 //     reference's own expressions (bit-identical values); a thread loads the 16 pairs it needs for its token and
@@ -16,7 +17,8 @@
 //   * thread = token (coalesced 128-byte warp loads straight from the sequence-fastest cache rows), per-channel
 //     premultiplied tables T[h][c][code] = (LUT*q[h,c], s_c*LUT*q[h,c^64]) in shared memory: 16 (8, 4) entries per
 //     channel are 16 distinct consecutive 8-byte slots -> conflict-free multicast for any code pattern.
-//   * per element: 1 code extract, 1 LDS.64, 2 FFMA.
+//   * per element: 1 address op (PRMT), 1 LDS.64, 1 packed FFMA2; words and rope values are prefetched into rotating
+//     register buffers; token ranges are cut at warp granularity so that every SM gets an equal share.
 #include "kvq_kscore.cuh"
 #include <stdlib.h>
 

@@ -7,7 +7,11 @@
 //
 //   O[h,c] = sum_t w[h,t] * (LUT[t, code(h,c,t)] (+) outlier(h,c,t))
 //
-// Design (DESIGN.md section 5):
+// This file: the generic per-token-LUT kernel (legacy op surface, and the fused path's fallback for shapes whose native
+// tile does not fit shared memory), the attend_init / attend_combine / attend_merge kernels, the TMA descriptor helper
+// and the kvq_attend entry points.  The native fused-path V kernel is kvq_vnative.cu.
+//
+// Design (DESIGN.md section 4.2):
 //   * one CTA streams a contiguous token range for ALL heads: the [H*W rows x 32 tokens] code slab of a tile is
 //     fetched by TMA (cp.async.bulk.tensor.2d, 128B swizzle) into a 2-4 stage shared-memory ring behind mbarriers,
 //     together with the tile's per-token LUT rows (cp.async.bulk); nothing is re-read;
