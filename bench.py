@@ -176,6 +176,9 @@ def main():
     ap.add_argument("--graph", default="dynamic", choices=["dynamic", "static"],
                     help="dynamic: cache length / position live on the device and every replay is the NEXT decode step "
                          "(growing cache); static: every replay re-runs the step at the captured length")
+    ap.add_argument("--sp-exchange", default="nccl", choices=["nccl", "p2p"],
+                    help="sp only: how the per-GPU partial attention results meet -- nccl: all_gather + merge kernel "
+                         "(default, validated); p2p: EXPERIMENTAL peer-memory exchange fused with the merge")
     ap.add_argument("--torch-profile", default="", help="write a per-kernel table of 3 graph replays to this file (diagnostic)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -256,6 +259,10 @@ def main():
         lo, hi = 0, cfg.n_layers
         stage = kd.DecoderStage(cfg, lo, hi, dev, quantizer, seed=0, with_head=True, sp=(rank, world))
         stage.global_pos = n_sink + L
+        if args.sp_exchange == "p2p":
+            from kvquant_b200.p2p import PeerExchange
+            stage.xchg = PeerExchange(rank, world, cfg.n_heads, dev)
+            config["sp_exchange"] = "p2p (experimental)"
     else:
         lo, hi = kd.partition_layers(cfg.n_layers, world, rank)
         stage = kd.DecoderStage(cfg, lo, hi, dev, quantizer, seed=0, with_head=(rank == 0))

@@ -201,6 +201,26 @@ KVQ_API int kvq_append_v_orig(int32_t* cache, const float* lut_tok, const float*
                       int32_t* out_count, int H, int64_t Lmax, int64_t slot, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * EXPERIMENTAL (not yet validated on a multi-GPU box; the default sequence-sharded path uses NCCL + kvq_attend_merge):
+ * exchange of the per-GPU partial attention results over NVLink peer memory, fused with their merge.
+ *   kvq_p2p_buffer_bytes(world, H)          size of one rank's exchange buffer
+ *   kvq_p2p_alloc / kvq_p2p_free            cudaMalloc'ed, zeroed buffer + its 64-byte CUDA IPC handle
+ *   kvq_p2p_open / kvq_p2p_close            map a peer's buffer from its handle
+ *   kvq_attend_exchange_merge               part = this rank's (out[H,128], lse[H]) from kvq_attend(out, out_lse);
+ *                                           peers_dev = DEVICE array of `world` buffer base pointers (own buffer at
+ *                                           index rank); seq_dev = device counter, advanced by one per call (all ranks
+ *                                           call in lockstep); out = merged [H,128]; *err_flag is set (and out is NaN)
+ *                                           if a peer did not arrive within ~2 s.
+ * ------------------------------------------------------------------------------------------------------------- */
+KVQ_API int64_t kvq_p2p_buffer_bytes(int world, int H);
+KVQ_API int kvq_p2p_alloc(void** ptr, int64_t bytes, void* ipc_handle_64);
+KVQ_API int kvq_p2p_open(const void* ipc_handle_64, void** ptr);
+KVQ_API int kvq_p2p_close(void* ptr);
+KVQ_API int kvq_p2p_free(void* ptr);
+KVQ_API int kvq_attend_exchange_merge(const float* part, void* const* peers_dev, int world, int rank, int H,
+                              int64_t* seq_dev, float* out, int32_t* err_flag, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Decode-harness helpers (kvquant_b200/decode.py; NOT part of the reference's quant_cuda surface): fused fp16
  * element-wise kernels around the hot path -- HF LlamaRMSNorm, rotate-half RoPE on Q + fp32 split of q/k/v
  * (modeling_llama.py:1851-1859), SwiGLU activation, fp32->fp16 cast.  Pointers named *_f16 are __half*.

@@ -98,6 +98,7 @@ class DecoderStage:
         self.sp = sp
         self.global_pos = None   # sp: absolute position of the new token (set by the driver)
         self.dyn = None          # device-resident length / position counters (enable_device_length)
+        self.xchg = None         # sp: optional kvquant_b200.p2p.PeerExchange (experimental) instead of NCCL all_gather
         gen = torch.Generator(device=self.device)
         gen.manual_seed(seed * 1000 + lo)
         self.layers = [DecoderLayer(cfg, self.device, gen, quantizer, with_sinks=(sp is None or sp[0] == 0))
@@ -205,9 +206,12 @@ class DecoderStage:
                         c.append_dyn(b["k"], b["v"], dyn["len"])
                     c.attend_dyn(qh, dyn["len"], 1 if owner else 0, rope_theta=cfg.rope_theta,
                                  out=part[:hid].view(H, HEAD_DIM), lse=part[hid:])
-                dist.all_gather_into_tensor(b["gath"], part)      # H*129 floats per rank over NVLink
                 o = b["om"]
-                _lib.check(lib.kvq_attend_merge(b["gath"].data_ptr(), world, H, o.data_ptr(), st))
+                if self.xchg is not None:                         # experimental: peer-memory exchange fused with the merge
+                    self.xchg.exchange_merge(part, o)
+                else:
+                    dist.all_gather_into_tensor(b["gath"], part)  # H*129 floats per rank over NVLink
+                    _lib.check(lib.kvq_attend_merge(b["gath"].data_ptr(), world, H, o.data_ptr(), st))
             x = self._gemv(ly.wo, o, 1, xs[flip], residual=x)
             flip ^= 1
             self._gemv(ly.wgu, x, 3, b["gu"], norm_w=ly.n2)
