@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define KVQ_ABI_VERSION 1
+#define KVQ_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define KVQ_API __attribute__((visibility("default")))
@@ -84,6 +84,8 @@ KVQ_API int kvq_append_v_sparse_parallel(int bits, int32_t* cache, const float* 
  * exactly the expressions of quant_cuda_kernel.cu:3081,3123-3126 evaluated once per (j,p) instead of once per
  * (head, channel, token).  float2 [64, n_pos]. */
 KVQ_API int kvq_rope_table_build(float* rope_cos_sin, float theta, int64_t n_pos, void* stream);
+/* The same table rounded once to fp16: half2 [64, n_pos] = (cos, sin) -- read by the fp16 mode of kvq_attend. */
+KVQ_API int kvq_rope_table_build_half(void* rope_half, float theta, int64_t n_pos, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Legacy decode matvecs (results are ADDED to `mul`, which the caller pre-zeroes -- modeling_llama.py:782,1209).
@@ -120,6 +122,11 @@ KVQ_API int kvq_v_matvec(int bits, const float* score, const int32_t* cache, flo
  * scratch: device buffer of kvq_attend_scratch_bytes(H, L) bytes.
  * sink_k: f16 [H,128,n_sink] post-RoPE keys, sink_v: f16 [H,n_sink,128] (modeling_llama.py:1464-1466), or NULL.
  * out: f32 [H,128].  out_lse (optional): f32 [H], log-sum-exp of the scaled scores over this call's tokens.
+ * rope_half selects the precision of the lookup tables (native V form only):
+ *   NULL      exact mode: fp32 tables everywhere, results equal to the legacy op chain to ~1e-6;
+ *   non-NULL  fp16 mode (north_star: "fp16 LUT", output within 1e-3): half2 table from kvq_rope_table_build_half
+ *             (same theta, same rope_npos); the K tables LUT*q, the V centroid pairs, cos/sin and the softmax
+ *             weights are fp16, every product is exact and every sum is fp32 (sm_100 mixed-precision FMA).
  * ------------------------------------------------------------------------------------------------------------- */
 KVQ_API int64_t kvq_attend_scratch_bytes(int H, int64_t L);
 KVQ_API int kvq_attend(int bits, const float* q,
@@ -130,7 +137,7 @@ KVQ_API int kvq_attend(int bits, const float* q,
                int n_out, int H, int64_t Lmax, int64_t L,
                const float* rope_cos_sin, int64_t rope_npos, float theta, int pos_offset,
                const void* sink_k, const void* sink_v, int n_sink,
-               float* out, float* out_lse, void* scratch, void* stream);
+               float* out, float* out_lse, void* scratch, const void* rope_half, void* stream);
 /* Merge of n_parts partial results of kvq_attend over disjoint token ranges (sequence-sharded decode):
  * parts f32 [n_parts, H*128 + H] = (out[H,128], lse[H]) per part, as produced with out_lse != NULL; out f32 [H,128]. */
 KVQ_API int kvq_attend_merge(const float* parts, int n_parts, int H, float* out, void* stream);
@@ -156,7 +163,7 @@ KVQ_API int kvq_attend_dyn(int bits, const float* q, const int32_t* kcache, cons
                    const float* v_outliers, const int32_t* v_outlier_idx, int n_out, int H, int64_t Lmax, int64_t L_cap,
                    const int64_t* len_dev, int64_t len_add, const float* rope_cos_sin, int64_t rope_npos, float theta,
                    int pos_offset, const void* sink_k, const void* sink_v, int n_sink, float* out, float* out_lse,
-                   void* scratch, void* stream);
+                   void* scratch, const void* rope_half, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Fused device-side append (native op): replaces the whole host round trip of

@@ -27,19 +27,20 @@ SIGNATURES = {
     "kvq_append_k_sparse_parallel": (_c_int, [_c_int, _p, _p, _p, _p, _p, _p, _c_int, _c_i64, _c_i64, _p]),
     "kvq_append_v_sparse_parallel": (_c_int, [_c_int, _p, _p, _p, _p, _p, _c_int, _c_i64, _c_i64, _p]),
     "kvq_rope_table_build": (_c_int, [_p, _c_f, _c_i64, _p]),
+    "kvq_rope_table_build_half": (_c_int, [_p, _c_f, _c_i64, _p]),
     "kvq_k_matvec": (_c_int, [_c_int, _p, _p, _p, _p, _c_int, _c_int, _c_i64, _c_i64, _p, _p, _c_int, _p, _c_i64,
                               _c_f, _c_int, _p]),
     "kvq_v_matvec": (_c_int, [_c_int, _p, _p, _p, _p, _c_int, _c_int, _c_i64, _c_i64, _p, _p, _c_int, _p]),
     "kvq_attend_scratch_bytes": (_c_i64, [_c_int, _c_i64]),
     "kvq_attend": (_c_int, [_c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_i64, _c_i64, _p,
-                            _c_i64, _c_f, _c_int, _p, _p, _c_int, _p, _p, _p, _p]),
+                            _c_i64, _c_f, _c_int, _p, _p, _c_int, _p, _p, _p, _p, _p]),
     "kvq_attend_merge": (_c_int, [_p, _c_int, _c_int, _p, _p]),
     "kvq_append_kv_fused": (_c_int, [_c_int, _c_int, _c_i64, _c_i64, _c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                      _p, _p, _p, _p, _p, _p, _p]),
     "kvq_append_kv_fused_dyn": (_c_int, [_c_int, _c_int, _c_i64, _p, _c_i64, _c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                          _p, _p, _p, _p, _p, _p, _p, _p]),
     "kvq_attend_dyn": (_c_int, [_c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_int, _c_i64, _c_i64, _p,
-                                _c_i64, _p, _c_i64, _c_f, _c_int, _p, _p, _c_int, _p, _p, _p, _p]),
+                                _c_i64, _p, _c_i64, _c_f, _c_int, _p, _p, _c_int, _p, _p, _p, _p, _p]),
     "kvq_p2p_buffer_bytes": (_c_i64, [_c_int, _c_int]),
     "kvq_p2p_alloc": (_c_int, [_p, _c_i64, _p]),
     "kvq_p2p_open": (_c_int, [_p, _p]),
@@ -80,7 +81,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if an export is missing: loud by design
         fn.restype = res
         fn.argtypes = args
-    if lib.kvq_abi_version() != 1:
+    if lib.kvq_abi_version() != 2:
         raise ImportError("kvquant_b200: ABI version mismatch")
     _lib = lib
     return lib

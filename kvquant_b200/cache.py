@@ -104,7 +104,12 @@ class LayerCache:
         self.pos_base = 0     # absolute position of slot 0 minus n_sink (non-zero for a sequence shard)
         self.sink_k = self.sink_v = None
         self._scratch = None
+        self._retired = []   # superseded scratch buffers (a captured graph may still point at them)
         self._out = torch.empty((self.H, HEAD_DIM), dtype=torch.float32, device=dev)
+        # lookup-table precision of the fused attend: "fp16" (north_star: fp16 LUT, output within 1e-3) or "fp32"
+        # (exact: equal to the legacy op chain to ~1e-6).  KVQ_EXACT=1 makes fp32 the default.
+        import os
+        self.precision = "fp32" if os.environ.get("KVQ_EXACT", "0") not in ("", "0") else "fp16"
 
     @classmethod
     def from_luts(cls, bits, num_heads, max_len, klut, v_cent, device="cuda", include_sparse=True,
@@ -148,6 +153,17 @@ class LayerCache:
         self.vaff[:, 0] = sf
         self.vaff[:, 1] = self.vlut[:, 0] - c0 * sf
 
+    def _ensure_scratch(self, need, slack):
+        """Attend scratch, grown on demand.  A superseded buffer is kept alive (never handed back to the allocator):
+        a captured CUDA graph bakes the raw pointer in, and growing must not happen inside a capture."""
+        if self._scratch is None or self._scratch.numel() < need:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("attend scratch must be sized before graph capture (run one eager attend / "
+                                   "attend_dyn with the same L_cap first)")
+            if self._scratch is not None:
+                self._retired.append(self._scratch)
+            self._scratch = torch.empty(int(need * slack) + 1024, dtype=torch.uint8, device=self.device)
+
     @_on_cache_device
     def append(self, k_new, v_new):
         """Quantise + pack + outlier split of one token's K and V, entirely on the device (one launch)."""
@@ -171,11 +187,10 @@ class LayerCache:
         position.  Returns f32 [H,128].  lse (optional f32 [H]) receives the log-sum-exp of the scaled scores, which
         lets partial results over disjoint token ranges be merged exactly (sequence-sharded decode)."""
         L = self.len
-        need = self.lib.kvq_attend_scratch_bytes(self.H, max(L, 1))
-        if self._scratch is None or self._scratch.numel() < need:
-            self._scratch = torch.empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=self.device)
+        self._ensure_scratch(self.lib.kvq_attend_scratch_bytes(self.H, max(L, 1)), 1.25)
         pos_offset = self.n_sink + self.pos_base
-        rope, npos = qc.rope_table(self.device, rope_theta, L + pos_offset + 1)
+        rope, rope_h, npos = qc.rope_tables(self.device, rope_theta, L + pos_offset + 1)
+        fast = self.precision == "fp16" and self.use_native_v
         out = self._out if out is None else out
         sp = self.include_sparse
         ns = self.n_sink if self.sink_k is not None else 0
@@ -188,7 +203,7 @@ class LayerCache:
             self.n_out, self.H, self.Lmax, L, rope.data_ptr(), npos, float(rope_theta), pos_offset,
             self.sink_k.data_ptr() if ns else None, self.sink_v.data_ptr() if ns else None, ns,
             out.data_ptr(), lse.data_ptr() if lse is not None else None, self._scratch.data_ptr(),
-            torch.cuda.current_stream().cuda_stream), "kvq_attend")
+            rope_h.data_ptr() if fast else None, torch.cuda.current_stream().cuda_stream), "kvq_attend")
         return out
 
     # -- device-resident length (one captured CUDA graph serves a growing cache) ----------------------
@@ -214,11 +229,10 @@ class LayerCache:
         if not self.use_native_v:
             raise NotImplementedError("device-resident length needs the native V form")
         L_cap = self.Lmax if L_cap is None else int(L_cap)
-        need = self.lib.kvq_attend_scratch_bytes(self.H, max(L_cap, 1))
-        if self._scratch is None or self._scratch.numel() < need:
-            self._scratch = torch.empty(int(need) + 1024, dtype=torch.uint8, device=self.device)
+        self._ensure_scratch(self.lib.kvq_attend_scratch_bytes(self.H, max(L_cap, 1)), 1.0)
         pos_offset = self.n_sink + self.pos_base
-        rope, npos = qc.rope_table(self.device, rope_theta, L_cap + pos_offset + 1)
+        rope, rope_h, npos = qc.rope_tables(self.device, rope_theta, L_cap + pos_offset + 1)
+        fast = self.precision == "fp16"
         out = self._out if out is None else out
         sp = self.include_sparse
         ns = self.n_sink if self.sink_k is not None else 0
@@ -231,7 +245,7 @@ class LayerCache:
             float(rope_theta), pos_offset, self.sink_k.data_ptr() if ns else None,
             self.sink_v.data_ptr() if ns else None, ns, out.data_ptr(),
             lse.data_ptr() if lse is not None else None, self._scratch.data_ptr(),
-            torch.cuda.current_stream().cuda_stream), "kvq_attend_dyn")
+            rope_h.data_ptr() if fast else None, torch.cuda.current_stream().cuda_stream), "kvq_attend_dyn")
         return out
 
     def bytes_per_token(self):

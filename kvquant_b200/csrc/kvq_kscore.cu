@@ -20,6 +20,7 @@
 //   * per element: 1 address op (PRMT), 1 LDS.64, 1 packed FFMA2; words and rope values are prefetched into rotating
 //     register buffers; token ranges are cut at warp granularity so that every SM gets an equal share.
 #include "kvq_kscore.cuh"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace kvq {
@@ -562,7 +563,7 @@ __global__ void __launch_bounds__(kOutPersThreads) k_outlier_pers_kernel(
     const float* __restrict__ q, const float* __restrict__ outliers, const int32_t* __restrict__ outlier_idx,
     float* __restrict__ out, int64_t stride_h, int64_t stride_t, int64_t L, int H, int n_out,
     const float2* __restrict__ rope, int64_t rope_npos, int pos_offset, float scale,
-    const int64_t* __restrict__ len_dev, int64_t len_add) {
+    const int64_t* __restrict__ len_dev, int64_t len_add, const uint32_t* __restrict__ rope_h) {
   extern __shared__ float2 s_qq[];                       // [H*128] = (q[c], q[c^64])
   if (len_dev != nullptr) {                              // device-resident length: L is the cap the grid was sized for
     const int64_t l = *len_dev + len_add;
@@ -588,7 +589,15 @@ __global__ void __launch_bounds__(kOutPersThreads) k_outlier_pers_kernel(
       const int c = col & (kHeadDim - 1);
       key = (int)(t * 64u) + h;                          // t < 2^25
       if (v != 0.f) {   // pads / non-outliers contribute exactly 0 in the reference too
-        const float2 cs = ld_keep_f2(rope + (int64_t)(c & (kHalf - 1)) * rope_npos + t + pos_offset, pol_keep);
+        float2 cs;
+        if (rope_h != nullptr) {   // fp16 mode: the half2 table the dense kernel streams (half the bytes per gather)
+          uint32_t u;
+          asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(u)
+                       : "l"(rope_h + (int64_t)(c & (kHalf - 1)) * rope_npos + t + pos_offset), "l"(pol_keep));
+          cs = __half22float2(*reinterpret_cast<const __half2*>(&u));
+        } else {
+          cs = ld_keep_f2(rope + (int64_t)(c & (kHalf - 1)) * rope_npos + t + pos_offset, pol_keep);
+        }
         const float2 qq = s_qq[col];
         const float sign = (c < kHalf) ? 1.f : -1.f;
         float dot = v * cs.x * qq.x;            // same operation order as DK.cu:513-515
@@ -654,7 +663,7 @@ static int launch_k_outliers(const KParams& p, int zero_first, float scale, cuda
   const int64_t sh = p.opart != nullptr ? 1 : p.out_stride, stt = p.opart != nullptr ? p.opart_stride : 1;
   k_outlier_pers_kernel<<<grid, kOutPersThreads, smem, st>>>(p.q, p.outliers, p.outlier_idx, dst, sh, stt, p.L,
                                                              p.H, p.n_out, p.rope, p.rope_npos, p.pos_offset, scale,
-                                                             p.len_dev, p.len_add);
+                                                             p.len_dev, p.len_add, p.rope_h);
   KVQ_LAUNCH_CHECK();
   return 0;
 }
@@ -754,6 +763,29 @@ int k_scores_fused(int bits, const float* q, const int32_t* cache, float* scores
     if (!tm) p.accumulate = 1;
   }
   return k_scores_dispatch(bits, p, st);
+}
+
+// fp16 mode of the fused attend (rope_half != null): outlier scatter straight into the head-major score buffer
+// (cleared first), then the fp16-table dense kernel folds it in: out = (partial + S) * scale.
+int k_scores_fused_fast(int bits, const float* q, const int32_t* cache, float* scores, int64_t score_stride,
+                        const float* lut, const float* outliers, const int32_t* outlier_idx, int n_out, int H,
+                        int64_t Lmax, int64_t L, const float* rope, const void* rope_half, int64_t rope_npos,
+                        int pos_offset, float* gmax, float scale, const int64_t* len_dev, int64_t len_add, void* qtab,
+                        cudaStream_t st) {
+  int accumulate = 0;
+  if (outliers != nullptr) {
+    KParams p{};
+    p.len_dev = len_dev; p.len_add = len_add;
+    p.q = q; p.out = scores; p.outliers = outliers; p.outlier_idx = outlier_idx;
+    p.rope = reinterpret_cast<const float2*>(rope); p.rope_h = static_cast<const uint32_t*>(rope_half);
+    p.Lmax = Lmax; p.L = L; p.out_stride = score_stride; p.rope_npos = rope_npos;
+    p.H = H; p.n_out = n_out; p.pos_offset = pos_offset;
+    const int rc = launch_k_outliers(p, /*zero_first=*/1, 1.f, st);
+    if (rc != 0) return rc;
+    accumulate = 1;
+  }
+  return k_fast_dispatch(bits, q, cache, scores, score_stride, lut, H, Lmax, L, rope_half, rope_npos, pos_offset, gmax,
+                         scale, accumulate, len_dev, len_add, qtab, st);
 }
 
 }  // namespace kvq

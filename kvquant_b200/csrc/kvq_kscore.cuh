@@ -23,6 +23,8 @@ struct KParams {
   int accumulate;            // 1: out = (out + S)*scale, 0: out = S*scale
   const float* opart;        // fused path: outlier partial sums, TOKEN-major [L][opart_stride] (null: none / in `out`)
   int opart_stride;          // floats per token row (H rounded up to 32: one 128-byte line per 32 heads)
+  const uint32_t* rope_h;    // optional half2 copy of the rope table (fp16 mode of the fused attend: the outlier scatter
+                             // gathers 4-byte entries from the table the dense kernel streams anyway)
 };
 
 // compile-time loop (immediate LDS offsets and PRMT selectors need constant expressions)
@@ -65,5 +67,9 @@ inline int64_t k_token_range(int64_t L, int64_t splits) {
 int k_pair_dispatch(int bits, const KParams& p, cudaStream_t st);
 // dense K-score kernel, 3-bit, carried words (kvq_k3.cu)
 int k_scores3_dispatch(const KParams& p, cudaStream_t st);
+// dense K-score kernel of the fused attend, fp16-table form (kvq_kfast.cu)
+int k_fast_dispatch(int bits, const float* q, const int32_t* cache, float* scores, int64_t score_stride, const float* lut,
+                    int H, int64_t Lmax, int64_t L, const void* rope_half, int64_t rope_npos, int pos_offset, float* gmax,
+                    float scale, int accumulate, const int64_t* len_dev, int64_t len_add, void* qtab, cudaStream_t st);
 
 }  // namespace kvq

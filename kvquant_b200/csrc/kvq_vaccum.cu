@@ -23,6 +23,7 @@
 //   * outliers scatter into a shared-memory accumulator (42 shared atomics per token instead of 42 global
 //     atomics onto 4096 hot addresses).
 #include "kvq_common.cuh"
+#include <stdlib.h>
 #include <cuda_fp16.h>
 #include <dlfcn.h>
 
@@ -521,6 +522,23 @@ int v_native_dispatch(int bits, const float* score, int64_t score_stride, const 
                       int n_out, int H, int64_t Lmax, int64_t L, float* out_o, float* out_l, int* n_cta,
                       const int64_t* len_dev, int64_t len_add, cudaStream_t st);
 
+int k_scores_fused_fast(int bits, const float* q, const int32_t* cache, float* scores, int64_t score_stride,
+                        const float* lut, const float* outliers, const int32_t* outlier_idx, int n_out, int H,
+                        int64_t Lmax, int64_t L, const float* rope, const void* rope_half, int64_t rope_npos,
+                        int pos_offset, float* gmax, float scale, const int64_t* len_dev, int64_t len_add, void* qtab,
+                        cudaStream_t st);
+int v_fast_dispatch(int bits, int half_mode, const float* score, int64_t score_stride, const float* gmax,
+                    const int32_t* cache, const float* v_cent, const float* v_aff, const float* outliers,
+                    const int32_t* outlier_idx, int n_out, int H, int64_t Lmax, int64_t L, float* out_o, float* out_l,
+                    int* n_cta, const int64_t* len_dev, int64_t len_add, cudaStream_t st);
+
+// KVQ_V_IMPL=native selects the round-1 V kernel (global RED outlier scatter) for A/B runs
+static int v_impl_native() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("KVQ_V_IMPL"); v = (e && e[0] == 'n') ? 1 : 0; }
+  return v;
+}
+
 static int check_v_common(int H, int64_t Lmax, int64_t L, const void* cache) {
   if (H <= 0 || (H & 3) != 0 || H > 64 || L < 0 || L > Lmax) return KVQ_E_SHAPE;
   if ((Lmax & 3) != 0 || (reinterpret_cast<uintptr_t>(cache) & 15) != 0) return KVQ_E_ALIGN;
@@ -564,9 +582,9 @@ static const int kMaxPart = 256;
 
 int64_t kvq_attend_scratch_bytes(int H, int64_t L) {
   // scores [H][L'] + gmax [H] + sink scores [H][64] + partial o / l of <= kMaxPart CTAs + token-major K-outlier
-  // partials [L'][H'] (H' = H rounded up to 32)
+  // partials [L'][H'] (H' = H rounded up to 32) + the premultiplied half2 K table [H][128][16] of the fp16 mode
   return 4 * ((int64_t)H * round_up(L, 32) + H + (int64_t)H * 64 + (int64_t)kMaxPart * H * kHeadDim + (int64_t)kMaxPart * H +
-              round_up(L, 32) * round_up(H, 32)) + 256;
+              round_up(L, 32) * round_up(H, 32) + (int64_t)H * kHeadDim * 16) + 256;
 }
 
 }  // extern "C"
@@ -575,7 +593,8 @@ static int attend_impl(int bits, const float* q, const int32_t* kcache, const fl
                const int32_t* k_outlier_idx, const int32_t* vcache, const float* vlut_tok, const float* v_cent,
                const float* v_aff, const float* v_outliers, const int32_t* v_outlier_idx, int n_out, int H, int64_t Lmax, int64_t L, const float* rope_cos_sin,
                int64_t rope_npos, float theta, int pos_offset, const void* sink_k, const void* sink_v, int n_sink,
-               float* out, float* out_lse, void* scratch, const int64_t* len_dev, int64_t len_add, void* stream) {
+               float* out, float* out_lse, void* scratch, const int64_t* len_dev, int64_t len_add, const void* rope_half,
+               void* stream) {
   if (!q || !kcache || !klut || !vcache || !rope_cos_sin || !out || !scratch) return KVQ_E_NULL;
   const bool native_v = (v_cent != nullptr && v_aff != nullptr);
   if (!native_v && !vlut_tok) return KVQ_E_NULL;
@@ -595,16 +614,25 @@ static int attend_impl(int bits, const float* q, const int32_t* kcache, const fl
   float* part_l = part_o + (int64_t)kMaxPart * H * kHeadDim;
   float* opart = part_l + (int64_t)kMaxPart * H;          // 16-byte aligned: every block above is a multiple of 4 floats
   const int opart_stride = (int)round_up(H, 32);
+  float* qtab = opart + round_up(L, 32) * opart_stride;    // 16-byte aligned (rows of 32 floats)
+  const bool fast = rope_half != nullptr;                  // fp16 tables (north_star's precision); NULL = exact fp32
   const float scale = 0.08838834764831845f;  // 1/sqrt(128)  (modeling_llama.py:1959,1973)
   attend_init_kernel<<<H, kHeadDim, 0, st>>>(q, static_cast<const __half*>(sink_k), n_sink, sink_scores, gmax, scale);
   KVQ_LAUNCH_CHECK();
   int n_cta = 0;
   if (L > 0) {
-    rc = k_scores_fused(bits, q, kcache, scores, stride, klut, k_outliers, k_outlier_idx, n_out, H, Lmax, L,
-                        rope_cos_sin, rope_npos, theta, pos_offset, gmax, scale, len_dev, len_add, opart, opart_stride, st);
+    if (fast)
+      rc = k_scores_fused_fast(bits, q, kcache, scores, stride, klut, k_outliers, k_outlier_idx, n_out, H, Lmax, L,
+                               rope_cos_sin, rope_half, rope_npos, pos_offset, gmax, scale, len_dev, len_add, qtab, st);
+    else
+      rc = k_scores_fused(bits, q, kcache, scores, stride, klut, k_outliers, k_outlier_idx, n_out, H, Lmax, L,
+                          rope_cos_sin, rope_npos, theta, pos_offset, gmax, scale, len_dev, len_add, opart, opart_stride, st);
     if (rc) return rc;
     rc = KVQ_E_UNSUPPORTED;
-    if (native_v)
+    if (native_v && !v_impl_native())
+      rc = v_fast_dispatch(bits, fast ? 1 : 0, scores, stride, gmax, vcache, v_cent, v_aff, v_outliers, v_outlier_idx,
+                           n_out, H, Lmax, L, part_o, part_l, &n_cta, len_dev, len_add, st);
+    if (rc == KVQ_E_UNSUPPORTED && native_v)
       rc = v_native_dispatch(bits, scores, stride, gmax, vcache, v_cent, v_aff, v_outliers, v_outlier_idx, n_out, H,
                              Lmax, L, part_o, part_l, &n_cta, len_dev, len_add, st);
     // shapes whose native tile does not fit shared memory (e.g. 13B at 4 bits) fall back to the per-token-LUT kernel
@@ -629,10 +657,10 @@ int kvq_attend(int bits, const float* q, const int32_t* kcache, const float* klu
                const int32_t* k_outlier_idx, const int32_t* vcache, const float* vlut_tok, const float* v_cent,
                const float* v_aff, const float* v_outliers, const int32_t* v_outlier_idx, int n_out, int H, int64_t Lmax, int64_t L, const float* rope_cos_sin,
                int64_t rope_npos, float theta, int pos_offset, const void* sink_k, const void* sink_v, int n_sink,
-               float* out, float* out_lse, void* scratch, void* stream) {
+               float* out, float* out_lse, void* scratch, const void* rope_half, void* stream) {
   return attend_impl(bits, q, kcache, klut, k_outliers, k_outlier_idx, vcache, vlut_tok, v_cent, v_aff, v_outliers,
                      v_outlier_idx, n_out, H, Lmax, L, rope_cos_sin, rope_npos, theta, pos_offset, sink_k, sink_v, n_sink,
-                     out, out_lse, scratch, nullptr, 0, stream);
+                     out, out_lse, scratch, nullptr, 0, rope_half, stream);
 }
 
 int kvq_attend_dyn(int bits, const float* q, const int32_t* kcache, const float* klut, const float* k_outliers,
@@ -640,12 +668,12 @@ int kvq_attend_dyn(int bits, const float* q, const int32_t* kcache, const float*
                    const float* v_outliers, const int32_t* v_outlier_idx, int n_out, int H, int64_t Lmax, int64_t L_cap,
                    const int64_t* len_dev, int64_t len_add, const float* rope_cos_sin, int64_t rope_npos, float theta,
                    int pos_offset, const void* sink_k, const void* sink_v, int n_sink, float* out, float* out_lse,
-                   void* scratch, void* stream) {
+                   void* scratch, const void* rope_half, void* stream) {
   if (!len_dev || !v_cent || !v_aff) return KVQ_E_NULL;
   if (L_cap <= 0) return KVQ_E_SHAPE;
   return attend_impl(bits, q, kcache, klut, k_outliers, k_outlier_idx, vcache, nullptr, v_cent, v_aff, v_outliers,
                      v_outlier_idx, n_out, H, Lmax, L_cap, rope_cos_sin, rope_npos, theta, pos_offset, sink_k, sink_v,
-                     n_sink, out, out_lse, scratch, len_dev, len_add, stream);
+                     n_sink, out, out_lse, scratch, len_dev, len_add, rope_half, stream);
 }
 
 int kvq_attend_merge(const float* parts, int n_parts, int H, float* out, void* stream) {

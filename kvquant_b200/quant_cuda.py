@@ -20,7 +20,8 @@ import torch
 from . import _lib
 
 _HEAD_DIM = 128
-_rope_tables = {}  # (device index, theta) -> (tensor [64, npos, 2] f32, npos)
+_rope_tables = {}  # (device index, theta) -> (f32 [64, npos, 2], half2 [64, npos] as int32, npos, build event)
+_rope_retired = []  # superseded tables stay allocated (graphs / other streams may still read them)
 
 
 def _stream():
@@ -56,19 +57,43 @@ def _cache_dims(mat, bits):
     return H, Lmax
 
 
-def rope_table(device, theta: float, min_npos: int):
-    """(tensor, npos) with npos >= min_npos; grown geometrically, rebuilt on the current stream."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), float(theta))
+def rope_tables(device, theta: float, min_npos: int):
+    """(f32 table [64, npos, 2], half2 table [64, npos] as int32, npos) with npos >= min_npos; grown geometrically.
+
+    Superseded tables are never freed: a captured CUDA graph (or a kernel still in flight on another stream) may hold
+    their raw pointers.  Both tables are built on the current stream; an event recorded after the build is waited on
+    by every later caller's stream, so a consumer on another stream never reads a half-built table."""
+    dev = device.index if device.index is not None else torch.cuda.current_device()
+    key = (dev, float(theta))
     cur = _rope_tables.get(key)
-    if cur is not None and cur[1] >= min_npos:
-        return cur
-    npos = max(int(min_npos), 2 * cur[1] if cur else 0, 4096)
-    npos = (npos + 255) // 256 * 256
-    t = torch.empty((64, npos, 2), dtype=torch.float32, device=device)
-    lib = _lib.load()
-    _lib.check(lib.kvq_rope_table_build(t.data_ptr(), float(theta), npos, _stream()), "kvq_rope_table_build")
-    _rope_tables[key] = (t, npos)
-    return _rope_tables[key]
+    if cur is None or cur[2] < min_npos:
+        npos = max(int(min_npos), 2 * cur[2] if cur else 0, 4096)
+        npos = (npos + 255) // 256 * 256
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("rope table for theta=%g must cover %d positions before graph capture "
+                               "(call rope_tables() once outside the capture)" % (theta, min_npos))
+        t = torch.empty((64, npos, 2), dtype=torch.float32, device=device)
+        th = torch.empty((64, npos), dtype=torch.int32, device=device)
+        lib = _lib.load()
+        with torch.cuda.device(device):
+            _lib.check(lib.kvq_rope_table_build(t.data_ptr(), float(theta), npos, _stream()), "kvq_rope_table_build")
+            _lib.check(lib.kvq_rope_table_build_half(th.data_ptr(), float(theta), npos, _stream()),
+                       "kvq_rope_table_build_half")
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+        if cur is not None:
+            _rope_retired.append(cur)
+        cur = (t, th, npos, ev)
+        _rope_tables[key] = cur
+    if not cur[3].query():
+        torch.cuda.current_stream(device).wait_event(cur[3])
+    return cur[0], cur[1], cur[2]
+
+
+def rope_table(device, theta: float, min_npos: int):
+    """(f32 tensor, npos) -- the table the legacy K ops read."""
+    t, _, npos = rope_tables(device, theta, min_npos)
+    return t, npos
 
 
 # ---------------------------------------------------------------------------------------------------------------

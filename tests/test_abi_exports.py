@@ -40,7 +40,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "missing export " + name
     assert sorted(_lib.SIGNATURES) == declared          # the ctypes table covers the header one to one
-    assert _lib.load().kvq_abi_version() == 1
+    assert _lib.load().kvq_abi_version() == 2
     assert b"bits" in _lib.load().kvq_error_string(-1)
 
 
@@ -92,7 +92,7 @@ def test_header_is_plain_c_and_links_against_the_library(tmp_path):
     subprocess.check_call(["gcc", "-std=c99", "-I", inc, str(src), lib, "-o", str(exe),
                            "-Wl,-rpath," + os.path.dirname(lib), "-Wl,-rpath,/usr/local/cuda/lib64"])
     out = subprocess.check_output([str(exe)], text=True).split(None, 1)
-    assert out[0] == "1" and out[1].strip()
+    assert out[0] == "2" and out[1].strip()
 
 
 def test_csr_growth_glue_matches_the_oracle():
