@@ -354,6 +354,9 @@ class QuantK(torch.nn.Module):
         self.klen += 1
         L = self.klen - self.first_few_fp16
         mul = torch.zeros((q.shape[0], q.shape[1], L), dtype=torch.float, device=q.device)
+        # (deliberate: the reference switches to lookup_table2 only in its 2-bit branch, modeling_llama.py:812-815; Q-Norm
+        # checkpoints exist for 2 bits only, and dequantising with the table the outlier residuals were taken against
+        # is the consistent choice at every width)
         lut = self.lookup_table2 if (self.norm and self.lookup_table2 is not None) else self.lookup_table
         if self.include_sparse:
             self._op("vecquant%dmatmul_nuq_perchannel_transposed_rope_mha_batched_fused_opt2")(
@@ -409,6 +412,10 @@ class QuantV(torch.nn.Module):
 
     def load_lookup_table(self, quantizer, include_sparse=True, sparsity_threshold=0.99, norm=False):
         """Only the sorted centroids are kept (modeling_llama.py:1054-1055); the per-token LUT is built on append."""
+        if norm:
+            # the reference dequantises 2-bit V through a second per-token table under Q-Norm (modeling_llama.py:1115-1118,
+            # 1151, 1235); this mirror does not carry it -- LayerCache(v_norm=...) is the Q-Norm path of this library
+            raise NotImplementedError("QuantV mirror: Q-Norm is served by LayerCache(v_norm=(normscale, normoffset))")
         self.lut = torch.as_tensor(np.asarray(quantizer[2][0], dtype=np.float32)).flatten().sort().values.to(self.vcache.device)
         self.include_sparse, self.sparsity_threshold, self.norm = include_sparse, sparsity_threshold, norm
 

@@ -539,6 +539,13 @@ static int v_impl_native() {
   return v;
 }
 
+// KVQ_V_HALF=0/1 overrides the V table precision of the fp16 mode (A/B runs); default: follows the mode
+static int v_half_override() {
+  static int v = -2;
+  if (v == -2) { const char* e = getenv("KVQ_V_HALF"); v = !e ? -1 : (e[0] == '0' ? 0 : 1); }
+  return v;
+}
+
 static int check_v_common(int H, int64_t Lmax, int64_t L, const void* cache) {
   if (H <= 0 || (H & 3) != 0 || H > 64 || L < 0 || L > Lmax) return KVQ_E_SHAPE;
   if ((Lmax & 3) != 0 || (reinterpret_cast<uintptr_t>(cache) & 15) != 0) return KVQ_E_ALIGN;
@@ -630,7 +637,7 @@ static int attend_impl(int bits, const float* q, const int32_t* kcache, const fl
     if (rc) return rc;
     rc = KVQ_E_UNSUPPORTED;
     if (native_v && !v_impl_native())
-      rc = v_fast_dispatch(bits, fast ? 1 : 0, scores, stride, gmax, vcache, v_cent, v_aff, v_outliers, v_outlier_idx,
+      rc = v_fast_dispatch(bits, (fast && v_half_override() != 0) ? 1 : 0, scores, stride, gmax, vcache, v_cent, v_aff, v_outliers, v_outlier_idx,
                            n_out, H, Lmax, L, part_o, part_l, &n_cta, len_dev, len_add, st);
     if (rc == KVQ_E_UNSUPPORTED && native_v)
       rc = v_native_dispatch(bits, scores, stride, gmax, vcache, v_cent, v_aff, v_outliers, v_outlier_idx, n_out, H,

@@ -11,13 +11,13 @@
 // lookup in a private pair table).  What changed is who does what (ncu on v_native: ~50 % of its shared-memory /
 // L1 wavefronts were the outlier reductions, `red.global.add.f32` per entry):
 //   * warps 0-15  dense lookups only.
-//   * warps 16-18 outliers: each owns a PRIVATE fp32 accumulator row in shared memory and walks the tile's
+//   * warps 16-17 outliers: each owns a PRIVATE fp32 accumulator row in shared memory and walks the tile's
 //     (value, index) stream 32 entries at a time with plain load / add / store -- race-free by construction (one
 //     warp per row; equal indices inside a 32-entry chunk are merged with match.any first), no atomics, no global
 //     clear / fence / read-back protocol, deterministic.  The rows live in the 128-byte holes of the pair table
 //     (its rows are 256 bytes apart because PRMT builds `index * 256`, but only 128 bytes of a row are table) and in
 //     whatever shared memory is left.
-//   * warp 19 (and 18 when H > 32) softmax weights of the NEXT tile: exp(s - max), w sf_t, denominators and the
+//   * warps 18-19 softmax weights of the NEXT tile (half of the heads each): exp(s - max), w sf_t, denominators and the
 //     sum_t w off_t terms in registers (lane = token), and the TMA issue.
 // HALF = true (the fp16 mode of kvq_attend): the pair table holds half2 {cent[lo], cent[hi]} (one 4-byte lookup = one
 // wavefront per 64 elements instead of two) and the weights are fp16 (scaled by 2^8 against underflow); products are
@@ -31,8 +31,8 @@ constexpr int kVFCompute = 512;                    // compute threads (16 warps)
 constexpr int kVFThreads = 640;                    // + warps 16..19
 constexpr int kVFT = 32;                           // tokens per stage
 constexpr int kVFMaxStages = 3;
-constexpr int kVFMaxAcc = 3;
-constexpr int kVFPre = 16;                         // outlier chunks a warp prefetches per tile
+constexpr int kVFMaxAcc = 2;
+constexpr int kVFPre = 32;                         // outlier steps (token, 32-entry part) a warp prefetches per tile
 constexpr float kVFHalfScale = 256.f;
 constexpr uint32_t kVFSmemBudget = 227u * 1024u;
 
@@ -53,7 +53,7 @@ struct VFParams {
   uint32_t acc_off[kVFMaxAcc];             // byte offset of accumulator a (from the aligned smem base)
   uint32_t acc_stride[kVFMaxAcc];          // bytes between consecutive 32-float rows (128 packed, 256 in table holes)
   uint32_t off_tab, off_w, off_ws, off_red, off_bar;
-  uint32_t n_out_magic;                    // ceil(2^32 / n_out)
+  uint32_t n_out_magic;                    // (unused)
 };
 
 template <int BITS> struct VFCfg {
@@ -151,7 +151,7 @@ __device__ __forceinline__ void vf_tile_unit(const unsigned char* stage, uint32_
   }
 }
 
-template <int BITS, bool HALF>
+template <int BITS, bool HALF, int HW>
 __global__ void __launch_bounds__(kVFThreads, 1) v_fast_kernel(const __grid_constant__ CUtensorMap tmap, const VFParams p) {
   using C = VFCfg<BITS>;
   constexpr int N = C::N, W = C::W, NP = C::NP, TABN = C::TABN;
@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(kVFThreads, 1) v_fast_kernel(const __grid_cons
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int rows = p.H * W;
   const uint32_t stage_bytes = (uint32_t)rows * (kVFT * 4);
-  float* s_w = reinterpret_cast<float*>(smem + p.off_w);           // [2][H][32]  w = exp(s - max)
+  float* s_w = reinterpret_cast<float*>(smem + p.off_w);           // [2][32][H+1]  w = exp(s - max), token-major, padded:
+                                                                    // written by lane = token, gathered by lane = entry (head varies)
   unsigned char* s_ws = smem + p.off_ws;                            // [2][H][32]  w * sf_t (f32, or f16 * 2^8)
   float* s_red = reinterpret_cast<float*>(smem + p.off_red);        // [2][H]      denominators, offset terms
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
@@ -168,7 +169,8 @@ __global__ void __launch_bounds__(kVFThreads, 1) v_fast_kernel(const __grid_cons
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = p.n_stages;
   const int hidden = p.H * kHeadDim;
-  const int n_w = p.H * kVFT;
+  const int ldw = p.H + 1;
+  const int n_w = ldw * kVFT;
   const bool has_out = p.outliers != nullptr && p.n_acc > 0;
 
   // ---- pair table: row i (256 bytes apart) -> {cent[i & (N-1)], cent[i >> BITS]}; fp32: 16 half-warp-private float2
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(kVFThreads, 1) v_fast_kernel(const __grid_cons
   const int nbox = rows / p.box_rows;
 
   // ---- roles (warp-uniform; each role keeps its own state and loop, all meet at the same named-barrier count) --------
-  const int w_first = (p.H > 32) ? 18 : 19;                          // weights warps: [w_first, 19]
+  constexpr int w_first = 18;                                        // weights warps 18, 19 (HW heads each at most)
   auto cta_sync = [] { asm volatile("bar.sync 0, %0;" ::"n"(kVFThreads) : "memory"); };
   __syncthreads();
 
@@ -307,12 +309,15 @@ __global__ void __launch_bounds__(kVFThreads, 1) v_fast_kernel(const __grid_cons
       unsigned char* dst = smem + (size_t)s * stage_bytes;
       for (int b = 0; b < nbox; ++b) tma_load_2d(dst + (size_t)b * p.box_rows * 128, &tmap, &s_bar[s], (int)t0, b * p.box_rows);
     };
-    constexpr int HW = 32;
-    const int wh0 = (warp == 19) ? 0 : 32;
-    const int wh1 = (warp == 19) ? min(p.H, 32) : p.H;
+    const int hsplit = (p.H + 1) >> 1;                                 // warp 19: heads [0, hsplit), warp 18: the rest
+    const int wh0 = (warp == 19) ? 0 : hsplit;
+    const int wh1 = (warp == 19) ? hsplit : p.H;
     float lacc[HW], oacc[HW];
 #pragma unroll
     for (int i = 0; i < HW; ++i) { lacc[i] = 0.f; oacc[i] = 0.f; }
+    // the per-head maxima sit in shared memory for the duration of the loop (s_red is free until the epilogue)
+    for (int h = wh0 + lane; h < wh1; h += 32) s_red[h] = p.gmax[h];
+    __syncwarp();
     auto make_weights = [&](int it) {     // weights of tile `it` -> buffer it & 1
       const int64_t t = (tile0 + it) * kVFT + lane;
       const bool ok = t < L_eff;
@@ -320,17 +325,27 @@ __global__ void __launch_bounds__(kVFThreads, 1) v_fast_kernel(const __grid_cons
       if (ok) aff = *reinterpret_cast<const float2*>(p.v_aff + 2 * t);
       float* wb = s_w + (it & 1) * n_w;
       unsigned char* wsb = s_ws + (size_t)(it & 1) * p.H * kWsRow;
+      const float* sp = p.score + t;
+      constexpr int HB = (HW > 16) ? 8 : 16;   // heads per batch: all their score loads in flight before any store
 #pragma unroll
-      for (int i = 0; i < HW; ++i) {
-        const int h = wh0 + i;
-        if (h < wh1) {
-          float w = 0.f;
-          if (ok) w = __expf(p.score[(int64_t)h * p.score_stride + t] - p.gmax[h]);
-          lacc[i] += w;
-          oacc[i] = fmaf(w, aff.y, oacc[i]);
-          wb[h * kVFT + lane] = w;
-          if constexpr (HALF) reinterpret_cast<__half*>(wsb + (size_t)h * kWsRow)[lane] = __float2half_rn(fminf(w * aff.x * kVFHalfScale, 65504.f));
-          else reinterpret_cast<float*>(wsb + (size_t)h * kWsRow)[lane] = w * aff.x;
+      for (int b = 0; b < HW; b += HB) {
+        float sc[HB];
+#pragma unroll
+        for (int i = 0; i < HB; ++i) {
+          const int h = wh0 + b + i;
+          sc[i] = (ok && h < wh1) ? __ldcg(sp + (int64_t)h * p.score_stride) : -INFINITY;
+        }
+#pragma unroll
+        for (int i = 0; i < HB; ++i) {
+          const int h = wh0 + b + i;
+          if (h < wh1) {
+            const float w = (sc[i] == -INFINITY) ? 0.f : __expf(sc[i] - s_red[h]);
+            lacc[b + i] += w;
+            oacc[b + i] = fmaf(w, aff.y, oacc[b + i]);
+            wb[lane * ldw + h] = w;
+            if constexpr (HALF) reinterpret_cast<__half*>(wsb + (size_t)h * kWsRow)[lane] = __float2half_rn(fminf(w * aff.x * kVFHalfScale, 65504.f));
+            else reinterpret_cast<float*>(wsb + (size_t)h * kWsRow)[lane] = w * aff.x;
+          }
         }
       }
     };
@@ -360,72 +375,86 @@ __global__ void __launch_bounds__(kVFThreads, 1) v_fast_kernel(const __grid_cons
     const bool active = has_out && oa < p.n_acc;
     const uint32_t my_acc = active ? smem_u32(smem + p.acc_off[oa]) : 0u;
     const uint32_t my_stride = active ? p.acc_stride[oa] : 0u;
+    // Token-aligned walk: warp `oa` owns tokens oa, oa + n_acc, ... of the tile; one step = up to 32 entries of ONE
+    // token's row.  The indices of a row are distinct, so the 32 lanes of a step touch 32 different accumulator
+    // words: plain load / add / store, no atomics and nothing to merge.  Steps of one warp hit the same private row in
+    // program order (same-address accesses of a warp are served in issue order; __syncwarp orders them formally).
+    const int steps_per_tok = (p.n_out + 31) >> 5;
+    const bool need_tail = p.n_out > 64 || (kVFT + p.n_acc - 1) / p.n_acc > kVFPre / 2;
     float opre_v[kVFPre];
     int opre_i[kVFPre];
-    auto tile_entries = [&](int it) -> int {        // live (value, index) entries of tile `it`
-      const int64_t t0 = (tile0 + it) * kVFT;
-      const int64_t nt = min((int64_t)kVFT, L_eff - t0);
-      return nt > 0 ? (int)nt * p.n_out : 0;
-    };
     auto load_outliers = [&](int it) {
-      const int E = tile_entries(it);
-      const int64_t e0 = (tile0 + it) * kVFT * (int64_t)p.n_out;
+      const int64_t t0 = (tile0 + it) * kVFT;
 #pragma unroll
       for (int k = 0; k < kVFPre; ++k) {
-        const int e = (oa + k * p.n_acc) * 32 + lane;
-        const bool in = e < E;
-        opre_v[k] = in ? __ldcs(p.outliers + e0 + e) : 0.f;
-        opre_i[k] = in ? __ldcs(p.outlier_idx + e0 + e) : 0;
+        const int tok = oa + (k / 2) * p.n_acc, part = k & 1;        // two steps per token cover n_out <= 64
+        const int e = part * 32 + lane;
+        const bool in = active && tok < kVFT && (t0 + tok) < L_eff && e < p.n_out && part < steps_per_tok;
+        const int64_t off = (t0 + tok) * p.n_out + e;
+        opre_v[k] = in ? __ldcs(p.outliers + off) : 0.f;
+        opre_i[k] = in ? __ldcs(p.outlier_idx + off) : 0;
       }
     };
-    auto scatter = [&](float v, int idx, int e, const float* wbuf) {
-      // x = w[head, token] * value, merged over equal indices inside the chunk, then one plain RMW per index
-      const int tl = (int)__umulhi((uint32_t)e, p.n_out_magic);
+    // a lane with nothing to add (row tail, token past the end, zero value) targets a private dummy word with x = 0,
+    // so that a step is straight-line code for the whole warp: no divergence, no reconvergence barriers
+    const uint32_t dummy = smem_u32(s_red) + (uint32_t)(2 * p.H + (warp - 16) * 32 + lane) * 4u;
+    auto scatter = [&](float v, int idx, int tok, const float* wbuf) {   // slow path (rows / tiles past the prefetch window)
       float x = 0.f;
-      int key = -1 - lane;
-      if (v != 0.f) { x = v * wbuf[(idx >> 7) * kVFT + tl]; key = idx; }
-      const unsigned m = __match_any_sync(0xffffffffu, key);
-      float sum = x;
-      unsigned rest = m & ~(1u << lane);
-      while (__any_sync(0xffffffffu, rest != 0u)) {
-        const int src = rest ? (__ffs(rest) - 1) : lane;
-        const float y = __shfl_sync(0xffffffffu, x, src);
-        if (rest) sum += y;
-        rest &= rest - 1u;
+      uint32_t a = dummy;
+      if (v != 0.f) {
+        x = v * wbuf[tok * ldw + (idx >> 7)];
+        a = my_acc + (uint32_t)(idx >> 5) * my_stride + (uint32_t)(idx & 31) * 4u;
       }
-      if (key >= 0 && lane == (__ffs(m) - 1)) {
-        const uint32_t a = my_acc + (uint32_t)(idx >> 5) * my_stride + (uint32_t)(idx & 31) * 4u;
-        float cur;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cur) : "r"(a) : "memory");
-        cur += sum;
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(cur) : "memory");
-      }
+      float cur;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cur) : "r"(a) : "memory");
+      cur += x;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(cur) : "memory");
       __syncwarp();
     };
     if (active && ntiles > 0) load_outliers(0);
     for (int it = 0; it < ntiles; ++it) {
       cta_sync();
       if (active) {
-        // this tile's entries were fetched during the previous one; fetch the next tile's before walking them
-        float cv[kVFPre];
-        int ci[kVFPre];
-#pragma unroll
-        for (int k = 0; k < kVFPre; ++k) { cv[k] = opre_v[k]; ci[k] = opre_i[k]; }
-        if (it + 1 < ntiles) load_outliers(it + 1);
-        const int E = tile_entries(it);
+        // this tile's entries were fetched at the end of the previous iteration (in flight across the barrier)
         const float* wbuf = s_w + (it & 1) * n_w;
-        const int nchunk = (E + 31) >> 5;
+        // per group of 8 steps -- phase 1 (independent per step, pipelines freely): x = value * w[head, token] and the
+        // accumulator address, written over the prefetched (value, index) registers; phase 2: one plain
+        // read-modify-write per step, in program order (the steps of this warp may hit the same word)
 #pragma unroll
-        for (int k = 0; k < kVFPre; ++k) {
-          const int c = oa + k * p.n_acc;
-          if (c < nchunk) scatter(cv[k], ci[k], c * 32 + lane, wbuf);
+        for (int k0 = 0; k0 < kVFPre; k0 += 8) {
+#pragma unroll
+          for (int k = k0; k < k0 + 8; ++k) {
+            const int tok = oa + (k / 2) * p.n_acc;
+            const float v = opre_v[k];
+            const int idx = opre_i[k];
+            const bool on = (tok < kVFT) && (v != 0.f);
+            opre_v[k] = on ? v * wbuf[tok * ldw + (idx >> 7)] : 0.f;
+            opre_i[k] = on ? (int)(my_acc + (uint32_t)(idx >> 5) * my_stride + (uint32_t)(idx & 31) * 4u) : (int)dummy;
+          }
+#pragma unroll
+          for (int k = k0; k < k0 + 8; ++k) {
+            float cur;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cur) : "r"(opre_i[k]) : "memory");
+            cur += opre_v[k];
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(opre_i[k]), "f"(cur) : "memory");
+            __syncwarp();
+          }
         }
-        const int64_t e0 = (tile0 + it) * kVFT * (int64_t)p.n_out;
-        for (int c = oa + kVFPre * p.n_acc; c < nchunk; c += p.n_acc) {     // rows wider than the prefetch window
-          const int e = c * 32 + lane;
-          const bool in = e < E;
-          scatter(in ? p.outliers[e0 + e] : 0.f, in ? p.outlier_idx[e0 + e] : 0, e, wbuf);
+        if (need_tail) {
+          // tokens past the prefetch window (a single outlier warp) and rows wider than 64 entries: straight from
+          // global memory
+          const int64_t t0 = (tile0 + it) * kVFT;
+          int slot = 0;
+          for (int tok = oa; tok < kVFT && t0 + tok < L_eff; tok += p.n_acc, ++slot) {
+            const bool pre = slot < kVFPre / 2;
+            for (int e = (pre ? 64 : 0) + lane; e - lane < p.n_out; e += 32) {
+              const bool in = e < p.n_out;
+              const int64_t off = (t0 + tok) * p.n_out + e;
+              scatter(in ? p.outliers[off] : 0.f, in ? p.outlier_idx[off] : 0, tok, wbuf);
+            }
+          }
         }
+        if (it + 1 < ntiles) load_outliers(it + 1);
       }
     }
     cta_sync();
@@ -435,7 +464,7 @@ __global__ void __launch_bounds__(kVFThreads, 1) v_fast_kernel(const __grid_cons
 
 int num_sms_cached();
 
-template <int BITS, bool HALF>
+template <int BITS, bool HALF, int HW>
 static int launch_vf(VFParams p, const int32_t* cache, int* n_cta_out, cudaStream_t st) {
   using C = VFCfg<BITS>;
   const int rows = p.H * C::W;
@@ -443,9 +472,9 @@ static int launch_vf(VFParams p, const int32_t* cache, int* n_cta_out, cudaStrea
   const uint32_t stage_bytes = (uint32_t)rows * (kVFT * 4);
   const uint32_t tab_span = (uint32_t)C::TABN * 256u;
   const uint32_t ws_bytes = 2u * p.H * (HALF ? kVFT * 2 : kVFT * 4);
-  const uint32_t w_bytes = 2u * p.H * kVFT * 4;
-  const uint32_t red_bytes = 2u * p.H * 4;
-  const int max_acc = (p.H > 32) ? 2 : kVFMaxAcc;      // warp 18 computes weights when H > 32
+  const uint32_t w_bytes = ((2u * (p.H + 1) * kVFT * 4) + 15u) & ~15u;
+  const uint32_t red_bytes = (2u * p.H + 64u) * 4;     // per-head scalars + one dummy word per outlier-warp lane
+  const int max_acc = kVFMaxAcc;
   const bool want_out = p.outliers != nullptr;
   int S = kVFMaxStages;
   for (; S >= 2; --S) {
@@ -486,7 +515,7 @@ static int launch_vf(VFParams p, const int32_t* cache, int* n_cta_out, cudaStrea
     static PerDeviceOnce attr_once;
     bool& attr_done = attr_once.cur();
     if (!attr_done) {
-      cudaError_t e = cudaFuncSetAttribute(v_fast_kernel<BITS, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVFSmemBudget);
+      cudaError_t e = cudaFuncSetAttribute(v_fast_kernel<BITS, HALF, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVFSmemBudget);
       if (e != cudaSuccess) return (int)e;
       attr_done = true;
     }
@@ -501,7 +530,7 @@ static int launch_vf(VFParams p, const int32_t* cache, int* n_cta_out, cudaStrea
     p.tiles_per_cta = (int)((n_tiles + sms - 1) / sms);
     const int n_cta = (int)((n_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta);
     p.n_out_magic = p.n_out > 0 ? (uint32_t)(((uint64_t)1 << 32) / (uint32_t)p.n_out + 1u) : 0u;
-    v_fast_kernel<BITS, HALF><<<n_cta, kVFThreads, total, st>>>(tmap, p);
+    v_fast_kernel<BITS, HALF, HW><<<n_cta, kVFThreads, total, st>>>(tmap, p);
     KVQ_LAUNCH_CHECK();
     *n_cta_out = n_cta;
     return 0;
@@ -519,13 +548,14 @@ int v_fast_dispatch(int bits, int half_mode, const float* score, int64_t score_s
   p.score = score; p.gmax = gmax; p.v_cent = v_cent; p.v_aff = v_aff; p.out_o = out_o; p.out_l = out_l;
   p.outliers = outliers; p.outlier_idx = outlier_idx; p.Lmax = Lmax; p.L = L; p.score_stride = score_stride;
   p.H = H; p.n_out = n_out;
+  const bool wide = H > 32;      // heads per weights warp: 16 (H <= 32) or 32 (H <= 64)
   switch (bits * 2 + (half_mode ? 1 : 0)) {
-    case 8: return launch_vf<4, false>(p, cache, n_cta, st);
-    case 9: return launch_vf<4, true>(p, cache, n_cta, st);
-    case 6: return launch_vf<3, false>(p, cache, n_cta, st);
-    case 7: return launch_vf<3, true>(p, cache, n_cta, st);
-    case 4: return launch_vf<2, false>(p, cache, n_cta, st);
-    case 5: return launch_vf<2, true>(p, cache, n_cta, st);
+    case 8: return wide ? launch_vf<4, false, 32>(p, cache, n_cta, st) : launch_vf<4, false, 16>(p, cache, n_cta, st);
+    case 9: return wide ? launch_vf<4, true, 32>(p, cache, n_cta, st) : launch_vf<4, true, 16>(p, cache, n_cta, st);
+    case 6: return wide ? launch_vf<3, false, 32>(p, cache, n_cta, st) : launch_vf<3, false, 16>(p, cache, n_cta, st);
+    case 7: return wide ? launch_vf<3, true, 32>(p, cache, n_cta, st) : launch_vf<3, true, 16>(p, cache, n_cta, st);
+    case 4: return wide ? launch_vf<2, false, 32>(p, cache, n_cta, st) : launch_vf<2, false, 16>(p, cache, n_cta, st);
+    case 5: return wide ? launch_vf<2, true, 32>(p, cache, n_cta, st) : launch_vf<2, true, 16>(p, cache, n_cta, st);
     default: return KVQ_E_BITS;
   }
 }

@@ -52,7 +52,8 @@ def main():
             q = torch.randn((H, 128), device=dev).half().float().contiguous()
             fbytes = L * caches[0].bytes_per_token()
             outs = {}
-            for prec in ("fp32", "fp16"):
+            precs = os.environ.get("PROBE_PREC", "fp32,fp16").split(",")
+            for prec in precs:
                 for lc in caches:
                     lc.precision = prec
                 for _ in range(2):
@@ -91,6 +92,10 @@ def main():
                          kernels=[dict(name=n, count=c, avg_us=round(u, 2)) for n, c, u in rows[:10]])
                 except Exception as ex:  # noqa: BLE001
                     emit(event="profiler_failed", err=repr(ex)[:200])
+            if len(outs) < 2:
+                del caches
+                torch.cuda.empty_cache()
+                continue
             d = (outs["fp16"] - outs["fp32"]).abs()
             ref = outs["fp32"].abs()
             emit(event="fp16_vs_fp32", bits=bits, L=L, max_rel=(d.max() / ref.max()).item(),
