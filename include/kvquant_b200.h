@@ -176,6 +176,10 @@ KVQ_API int kvq_attend_dyn(int bits, const float* q, const int32_t* kcache, cons
  *   `slot` receives (sf, off); v_cent_deq (optional): Q-Norm centroids cent*normscale+normoffset -- the outlier
  *   residual is taken against LUT2_t[zp] = v_cent_deq[zp]*sf+off (modeling_llama.py:1115-1118,1149-1152).
  *   Cache words at `slot` are OVERWRITTEN (not added).  Outlier rows (f32/i32 [Lmax, 2*n_each]) row `slot` written.
+ *   k_outliers / k_outlier_idx (and likewise the V pair) may be NULL: that cache is then dense-only -- the reference's
+ *   include_sparse=False branch (modeling_llama.py:753-779, 1178-1201): every K value keeps its nearest code, the V
+ *   range is the min / max of the vector (compute_lut, modeling_llama.py:318-349).  BASELINE configs[3] (dense-only)
+ *   and configs[4] (K outliers only) use this.
  * ------------------------------------------------------------------------------------------------------------- */
 KVQ_API int kvq_append_kv_fused(int bits, int H, int64_t Lmax, int64_t slot, int n_each,
                         const float* k_new, int32_t* kcache, const float* klut, const float* klut_sub,

@@ -65,7 +65,7 @@ class LayerCache:
     """Native quantised K+V cache of one layer (reference-compatible tensor layouts)."""
 
     def __init__(self, bits, num_heads, max_len, klut, klut_sub, thr_lower, thr_upper, v_cent, device,
-                 include_sparse=True, sparsity_threshold=0.99, n_sink=0, v_norm=None):
+                 include_sparse=True, sparsity_threshold=0.99, n_sink=0, v_norm=None, sparse_v=None):
         self.lib = _lib.load()
         self.bits, self.H, self.Lmax = int(bits), int(num_heads), int(max_len)
         if self.Lmax % 4:
@@ -74,7 +74,11 @@ class LayerCache:
         self.device = torch.device(device)
         if self.device.type == "cuda" and self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        self.include_sparse = include_sparse
+        # include_sparse: outlier rows for K (and for V unless sparse_v=False: BASELINE configs[4] keeps capped K
+        # outliers only); include_sparse=False is the reference's dense-only branch (configs[3])
+        self.include_sparse = bool(include_sparse)
+        self.sparse_k = self.include_sparse
+        self.sparse_v = self.include_sparse if sparse_v is None else (bool(sparse_v) and self.include_sparse)
         self.n_each = n_outliers_each(self.hidden, sparsity_threshold)
         self.n_out = 2 * self.n_each
         W = HEAD_DIM * bits // 32
@@ -95,10 +99,12 @@ class LayerCache:
         # per-token affine map (sf_t, off_t): LUT_t = v_cent*sf_t + off_t  -- what the native V kernel consumes
         self.vaff = torch.zeros((self.Lmax, 2), dtype=torch.float32, device=dev)
         self.use_native_v = True
-        self.k_outliers = torch.zeros((self.Lmax, self.n_out), dtype=torch.float32, device=dev)
-        self.k_outlier_idx = torch.zeros((self.Lmax, self.n_out), dtype=torch.int32, device=dev)
-        self.v_outliers = torch.zeros((self.Lmax, self.n_out), dtype=torch.float32, device=dev)
-        self.v_outlier_idx = torch.zeros((self.Lmax, self.n_out), dtype=torch.int32, device=dev)
+        def rows(on):   # a dense-only cache allocates no outlier rows (1M-token configs: 2 x 0.4 GB per layer saved)
+            n = self.Lmax if on else 1
+            return (torch.zeros((n, self.n_out), dtype=torch.float32, device=dev),
+                    torch.zeros((n, self.n_out), dtype=torch.int32, device=dev))
+        self.k_outliers, self.k_outlier_idx = rows(self.sparse_k)
+        self.v_outliers, self.v_outlier_idx = rows(self.sparse_v)
         self.len = 0          # tokens in the quantised cache
         self.n_sink = int(n_sink)
         self.pos_base = 0     # absolute position of slot 0 minus n_sink (non-zero for a sequence shard)
@@ -113,7 +119,7 @@ class LayerCache:
 
     @classmethod
     def from_luts(cls, bits, num_heads, max_len, klut, v_cent, device="cuda", include_sparse=True,
-                  sparsity_threshold=0.99, n_sink=0, v_norm=None):
+                  sparsity_threshold=0.99, n_sink=0, v_norm=None, sparse_v=None):
         """klut: mapping with 'lut' [hidden, n] (and optional 'lut2'), 'thr_lower', 'thr_upper' (numpy or torch)."""
         def t(x):
             return torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(device).float().contiguous()
@@ -121,7 +127,7 @@ class LayerCache:
         lut2 = t(klut["lut2"]).view(num_heads * HEAD_DIM, -1) if klut.get("lut2") is not None else None
         return cls(bits, num_heads, max_len, lut, lut2, t(klut["thr_lower"]), t(klut["thr_upper"]),
                    t(np.sort(np.asarray(v_cent.cpu() if torch.is_tensor(v_cent) else v_cent).ravel())), device,
-                   include_sparse, sparsity_threshold, n_sink, v_norm)
+                   include_sparse, sparsity_threshold, n_sink, v_norm, sparse_v)
 
     def reset(self):
         self.len = 0
@@ -140,8 +146,10 @@ class LayerCache:
         def put(dst, a):
             dst.copy_(torch.as_tensor(np.ascontiguousarray(a)).view(dst.shape) if not torch.is_tensor(a) else a.view(dst.shape))
         put(self.kcache, src.kwords); put(self.vcache, src.vwords); put(self.vlut, src.vlut)
-        put(self.k_outliers, src.k_out); put(self.k_outlier_idx, src.k_idx)
-        put(self.v_outliers, src.v_out); put(self.v_outlier_idx, src.v_idx)
+        if self.sparse_k:
+            put(self.k_outliers, src.k_out); put(self.k_outlier_idx, src.k_idx)
+        if self.sparse_v:
+            put(self.v_outliers, src.v_out); put(self.v_outlier_idx, src.v_idx)
         self.len = int(src.len)
         self.derive_vaff()
 
@@ -152,6 +160,12 @@ class LayerCache:
         sf = (self.vlut[:, -1] - self.vlut[:, 0]) / (c1 - c0)
         self.vaff[:, 0] = sf
         self.vaff[:, 1] = self.vlut[:, 0] - c0 * sf
+
+    def _out_ptrs(self, which):
+        """(values, indices) device pointers of a cache's outlier rows, or (None, None) when that cache is dense-only."""
+        if which == "k":
+            return (self.k_outliers.data_ptr(), self.k_outlier_idx.data_ptr()) if self.sparse_k else (None, None)
+        return (self.v_outliers.data_ptr(), self.v_outlier_idx.data_ptr()) if self.sparse_v else (None, None)
 
     def _ensure_scratch(self, need, slack):
         """Attend scratch, grown on demand.  A superseded buffer is kept alive (never handed back to the allocator):
@@ -167,18 +181,16 @@ class LayerCache:
     @_on_cache_device
     def append(self, k_new, v_new):
         """Quantise + pack + outlier split of one token's K and V, entirely on the device (one launch)."""
-        if not self.include_sparse:
-            raise NotImplementedError("dense-only native append: use QuantK/QuantV (legacy ops)")
         if self.len >= self.Lmax:
             raise IndexError("cache full")
         s = torch.cuda.current_stream().cuda_stream
         _lib.check(self.lib.kvq_append_kv_fused(
             self.bits, self.H, self.Lmax, self.len, self.n_each,
             qc._f32(k_new, "k_new"), self.kcache.data_ptr(), self.klut.data_ptr(), self.klut_sub.data_ptr(),
-            self.thr_lower.data_ptr(), self.thr_upper.data_ptr(), self.k_outliers.data_ptr(),
-            self.k_outlier_idx.data_ptr(), qc._f32(v_new, "v_new"), self.vcache.data_ptr(), self.v_cent.data_ptr(),
-            self.v_cent_deq.data_ptr() if self.v_norm is not None else None, self.vlut.data_ptr(), self.vaff.data_ptr(), self.v_outliers.data_ptr(), self.v_outlier_idx.data_ptr(), s),
-            "kvq_append_kv_fused")
+            self.thr_lower.data_ptr(), self.thr_upper.data_ptr(), *self._out_ptrs("k"),
+            qc._f32(v_new, "v_new"), self.vcache.data_ptr(), self.v_cent.data_ptr(),
+            self.v_cent_deq.data_ptr() if self.v_norm is not None else None, self.vlut.data_ptr(), self.vaff.data_ptr(),
+            *self._out_ptrs("v"), s), "kvq_append_kv_fused")
         self.len += 1
 
     @_on_cache_device
@@ -192,14 +204,12 @@ class LayerCache:
         rope, rope_h, npos = qc.rope_tables(self.device, rope_theta, L + pos_offset + 1)
         fast = self.precision == "fp16" and self.use_native_v
         out = self._out if out is None else out
-        sp = self.include_sparse
         ns = self.n_sink if self.sink_k is not None else 0
         _lib.check(self.lib.kvq_attend(
-            self.bits, qc._f32(q, "q"), self.kcache.data_ptr(), self.klut_deq.data_ptr(),
-            self.k_outliers.data_ptr() if sp else None, self.k_outlier_idx.data_ptr() if sp else None,
+            self.bits, qc._f32(q, "q"), self.kcache.data_ptr(), self.klut_deq.data_ptr(), *self._out_ptrs("k"),
             self.vcache.data_ptr(), self.vlut.data_ptr(),
             self.v_cent_deq.data_ptr() if self.use_native_v else None, self.vaff.data_ptr() if self.use_native_v else None,
-            self.v_outliers.data_ptr() if sp else None, self.v_outlier_idx.data_ptr() if sp else None,
+            *self._out_ptrs("v"),
             self.n_out, self.H, self.Lmax, L, rope.data_ptr(), npos, float(rope_theta), pos_offset,
             self.sink_k.data_ptr() if ns else None, self.sink_v.data_ptr() if ns else None, ns,
             out.data_ptr(), lse.data_ptr() if lse is not None else None, self._scratch.data_ptr(),
@@ -211,16 +221,14 @@ class LayerCache:
     def append_dyn(self, k_new, v_new, len_dev, slot_add=0):
         """append() at slot `len_dev[0] + slot_add`, the length read on the device.  The host-side `len` is NOT
         advanced: the caller owns the device counter (kvq_dec_counter_add) and re-syncs `len` when it leaves the graph."""
-        if not self.include_sparse:
-            raise NotImplementedError("dense-only native append: use QuantK/QuantV (legacy ops)")
         s = torch.cuda.current_stream().cuda_stream
         _lib.check(self.lib.kvq_append_kv_fused_dyn(
             self.bits, self.H, self.Lmax, len_dev.data_ptr(), int(slot_add), self.n_each,
             qc._f32(k_new, "k_new"), self.kcache.data_ptr(), self.klut.data_ptr(), self.klut_sub.data_ptr(),
-            self.thr_lower.data_ptr(), self.thr_upper.data_ptr(), self.k_outliers.data_ptr(),
-            self.k_outlier_idx.data_ptr(), qc._f32(v_new, "v_new"), self.vcache.data_ptr(), self.v_cent.data_ptr(),
+            self.thr_lower.data_ptr(), self.thr_upper.data_ptr(), *self._out_ptrs("k"),
+            qc._f32(v_new, "v_new"), self.vcache.data_ptr(), self.v_cent.data_ptr(),
             self.v_cent_deq.data_ptr() if self.v_norm is not None else None, self.vlut.data_ptr(), self.vaff.data_ptr(),
-            self.v_outliers.data_ptr(), self.v_outlier_idx.data_ptr(), s), "kvq_append_kv_fused_dyn")
+            *self._out_ptrs("v"), s), "kvq_append_kv_fused_dyn")
 
     @_on_cache_device
     def attend_dyn(self, q, len_dev, len_add=0, rope_theta=10000.0, out=None, lse=None, L_cap=None):
@@ -234,13 +242,10 @@ class LayerCache:
         rope, rope_h, npos = qc.rope_tables(self.device, rope_theta, L_cap + pos_offset + 1)
         fast = self.precision == "fp16"
         out = self._out if out is None else out
-        sp = self.include_sparse
         ns = self.n_sink if self.sink_k is not None else 0
         _lib.check(self.lib.kvq_attend_dyn(
-            self.bits, qc._f32(q, "q"), self.kcache.data_ptr(), self.klut_deq.data_ptr(),
-            self.k_outliers.data_ptr() if sp else None, self.k_outlier_idx.data_ptr() if sp else None,
-            self.vcache.data_ptr(), self.v_cent_deq.data_ptr(), self.vaff.data_ptr(),
-            self.v_outliers.data_ptr() if sp else None, self.v_outlier_idx.data_ptr() if sp else None,
+            self.bits, qc._f32(q, "q"), self.kcache.data_ptr(), self.klut_deq.data_ptr(), *self._out_ptrs("k"),
+            self.vcache.data_ptr(), self.v_cent_deq.data_ptr(), self.vaff.data_ptr(), *self._out_ptrs("v"),
             self.n_out, self.H, self.Lmax, L_cap, len_dev.data_ptr(), int(len_add), rope.data_ptr(), npos,
             float(rope_theta), pos_offset, self.sink_k.data_ptr() if ns else None,
             self.sink_v.data_ptr() if ns else None, ns, out.data_ptr(),
@@ -251,8 +256,7 @@ class LayerCache:
     def bytes_per_token(self):
         """Algorithmic HBM bytes one decode step reads per cached token (SURVEY.md 8d formula)."""
         b = 2 * self.H * HEAD_DIM * self.bits // 8 + 4 * 2 ** self.bits
-        if self.include_sparse:
-            b += 2 * self.n_out * 8
+        b += (int(self.sparse_k) + int(self.sparse_v)) * self.n_out * 8
         return b
 
 

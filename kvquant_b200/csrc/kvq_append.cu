@@ -298,6 +298,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) append_kv_fused_kernel(
   __shared__ float s_vzp;   // value the zero-point code dequantises to (Q-Norm: from the shifted centroids)
   const int tid = threadIdx.x;
   const bool isV = blockIdx.x == 1;
+  // a cache without an outlier row pointer is dense-only (the reference's include_sparse=False branch,
+  // modeling_llama.py:753-779, 1178-1201): K keeps every value as its nearest code, V's range is the min / max of
+  // the vector (compute_lut, modeling_llama.py:318-349) -- which is the order-statistics rule below with n_each = 0
+  if ((isV ? v_out : k_out) == nullptr) n_each = 0;
   const int n_out = 2 * n_each;
 
   if (!isV) {
@@ -317,8 +321,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) append_kv_fused_kernel(
       s_key[j] = f2key(r);
     }
     __syncthreads();
-    radix_select_both(s_key, hidden, n_each, sel);
-    collect_selected(s_key, hidden, n_each, sel, s_sel_idx, s_cnt);
+    if (n_each > 0) {
+      radix_select_both(s_key, hidden, n_each, sel);
+      collect_selected(s_key, hidden, n_each, sel, s_sel_idx, s_cnt);
+    }
     // values: k - LUT end entry, zeroed when |r| <= 1 (modeling_llama.py:730-747)
     if (tid < n_out) {
       const int j = s_sel_idx[tid];
@@ -418,6 +424,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) append_kv_fused_kernel(
     cache[(int64_t)R * Lmax + slot] = w;
   }
   // ---- outlier row, sorted by channel index (rank by counting; indices are distinct except pads) -----------
+  if (n_out == 0) return;
   float* orow = (isV ? v_out : k_out) + slot * n_out;
   int32_t* irow = (isV ? v_idx : k_idx) + slot * n_out;
   if (tid < n_out) {
@@ -553,13 +560,17 @@ static int append_kv_fused_impl(int bits, int H, int64_t Lmax, int64_t slot, con
                                 int32_t* k_outlier_idx, const float* v_new, int32_t* vcache, const float* v_cent,
                                 const float* v_cent_deq, float* vlut_tok, float* v_aff, float* v_outliers,
                                 int32_t* v_outlier_idx, void* stream) {
-  if (!k_new || !kcache || !klut || !klut_sub || !k_thr_lower || !k_thr_upper || !k_outliers || !k_outlier_idx ||
-      !v_new || !vcache || !v_cent || !vlut_tok || !v_outliers || !v_outlier_idx)
+  if (!k_new || !kcache || !klut || !klut_sub || !k_thr_lower || !k_thr_upper || !v_new || !vcache || !v_cent || !vlut_tok)
+    return KVQ_E_NULL;
+  // outlier rows are optional per cache: NULL = that cache is dense-only (value and index pointers go together)
+  if ((k_outliers == nullptr) != (k_outlier_idx == nullptr) || (v_outliers == nullptr) != (v_outlier_idx == nullptr))
     return KVQ_E_NULL;
   const int hidden = H * kHeadDim;
   if (H <= 0 || hidden > kMaxHidden || Lmax <= 0) return KVQ_E_SHAPE;
   if (slot_dev == nullptr && (slot < 0 || slot >= Lmax)) return KVQ_E_SHAPE;
-  if (n_each <= 0 || 2 * n_each > kMaxOut || 2 * (n_each + 1) > hidden) return KVQ_E_SHAPE;
+  const bool any_sparse = k_outliers != nullptr || v_outliers != nullptr;
+  if (any_sparse && (n_each <= 0 || 2 * n_each > kMaxOut || 2 * (n_each + 1) > hidden)) return KVQ_E_SHAPE;
+  if (!any_sparse) n_each = 0;
   if ((reinterpret_cast<uintptr_t>(klut) & 15) != 0) return KVQ_E_ALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint32_t* kc = reinterpret_cast<uint32_t*>(kcache);

@@ -527,25 +527,6 @@ int k_scores_fused_fast(int bits, const float* q, const int32_t* cache, float* s
                         int64_t Lmax, int64_t L, const float* rope, const void* rope_half, int64_t rope_npos,
                         int pos_offset, float* gmax, float scale, const int64_t* len_dev, int64_t len_add, void* qtab,
                         cudaStream_t st);
-int v_fast_dispatch(int bits, int half_mode, const float* score, int64_t score_stride, const float* gmax,
-                    const int32_t* cache, const float* v_cent, const float* v_aff, const float* outliers,
-                    const int32_t* outlier_idx, int n_out, int H, int64_t Lmax, int64_t L, float* out_o, float* out_l,
-                    int* n_cta, const int64_t* len_dev, int64_t len_add, cudaStream_t st);
-
-// KVQ_V_IMPL=native selects the round-1 V kernel (global RED outlier scatter) for A/B runs
-static int v_impl_native() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("KVQ_V_IMPL"); v = (e && e[0] == 'n') ? 1 : 0; }
-  return v;
-}
-
-// KVQ_V_HALF=0/1 overrides the V table precision of the fp16 mode (A/B runs); default: follows the mode
-static int v_half_override() {
-  static int v = -2;
-  if (v == -2) { const char* e = getenv("KVQ_V_HALF"); v = !e ? -1 : (e[0] == '0' ? 0 : 1); }
-  return v;
-}
-
 static int check_v_common(int H, int64_t Lmax, int64_t L, const void* cache) {
   if (H <= 0 || (H & 3) != 0 || H > 64 || L < 0 || L > Lmax) return KVQ_E_SHAPE;
   if ((Lmax & 3) != 0 || (reinterpret_cast<uintptr_t>(cache) & 15) != 0) return KVQ_E_ALIGN;
@@ -636,10 +617,7 @@ static int attend_impl(int bits, const float* q, const int32_t* kcache, const fl
                           rope_cos_sin, rope_npos, theta, pos_offset, gmax, scale, len_dev, len_add, opart, opart_stride, st);
     if (rc) return rc;
     rc = KVQ_E_UNSUPPORTED;
-    if (native_v && !v_impl_native())
-      rc = v_fast_dispatch(bits, (fast && v_half_override() != 0) ? 1 : 0, scores, stride, gmax, vcache, v_cent, v_aff, v_outliers, v_outlier_idx,
-                           n_out, H, Lmax, L, part_o, part_l, &n_cta, len_dev, len_add, st);
-    if (rc == KVQ_E_UNSUPPORTED && native_v)
+    if (native_v)
       rc = v_native_dispatch(bits, scores, stride, gmax, vcache, v_cent, v_aff, v_outliers, v_outlier_idx, n_out, H,
                              Lmax, L, part_o, part_l, &n_cta, len_dev, len_add, st);
     // shapes whose native tile does not fit shared memory (e.g. 13B at 4 bits) fall back to the per-token-LUT kernel

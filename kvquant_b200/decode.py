@@ -8,8 +8,9 @@ LlamaFlashAttention2.forward at q_len == 1 (modeling_llama.py:1778-2011):
     v/q/k proj -> RoPE on Q only -> append pre-RoPE K and V (quantise + outlier split) -> Q.K^T over the
     compressed cache (+ fp16 sinks) -> softmax -> .V -> o_proj -> MLP
 
-with random-init fp16 weights of the LLaMA architecture.  The dense GEMVs are plain library calls (cuBLAS through
-torch); everything that touches the KV cache goes through the C ABI (kvq_append_kv_fused, kvq_attend).
+with random-init fp16 weights of the LLaMA architecture.  The dense GEMVs are the library's own fused kernels
+(kvq_dec_gemv: RMSNorm / SwiGLU / residual folded in); everything that touches the KV cache goes through the C ABI
+(kvq_append_kv_fused, kvq_attend).
 
 Multi-GPU: the reference's only parallelism is naive layer-group model parallelism
 (`LlamaModel.set_devices`, modeling_llama.py:2428-2453: len(layers)//n_gpus consecutive layers per device, hidden
@@ -41,6 +42,7 @@ class DecodeConfig:
     n_sink: int = 0            # first_few_fp16
     sparsity_threshold: float = 0.99
     include_sparse: bool = True
+    sparse_v: bool = True      # False: outlier rows for K only (BASELINE configs[4]: capped K outliers)
     max_len: int = 4096        # quantised slots allocated per layer
 
     @staticmethod
@@ -79,7 +81,8 @@ class DecoderLayer:
         self.n2 = torch.ones(h, dtype=torch.float16, device=device)
         self.cache = LayerCache.from_luts(cfg.bits, cfg.n_heads, cfg.max_len, quantizer["klut"], quantizer["v_cent"],
                                           device=device, include_sparse=cfg.include_sparse,
-                                          sparsity_threshold=cfg.sparsity_threshold, n_sink=cfg.n_sink)
+                                          sparsity_threshold=cfg.sparsity_threshold, n_sink=cfg.n_sink,
+                                          sparse_v=cfg.sparse_v)
         if cfg.n_sink and with_sinks:
             sk = (torch.randn((cfg.n_heads, HEAD_DIM, cfg.n_sink), generator=gen, device=device)).half()
             sv = (torch.randn((cfg.n_heads, cfg.n_sink, HEAD_DIM), generator=gen, device=device)).half()
@@ -332,7 +335,8 @@ class GraphedStage:
 def layer_step_bytes(cfg: DecodeConfig, L: int):
     """Algorithmic HBM bytes of one layer's fused attend at cache length L."""
     n_out = 2 * (int(((1 - cfg.sparsity_threshold) / 2) * cfg.hidden) + 1)
-    per_tok = 2 * cfg.hidden * cfg.bits // 8 + 4 * 2 ** cfg.bits + (16 * n_out if cfg.include_sparse else 0)
+    n_sparse = (2 if cfg.sparse_v else 1) if cfg.include_sparse else 0
+    per_tok = 2 * cfg.hidden * cfg.bits // 8 + 4 * 2 ** cfg.bits + 8 * n_out * n_sparse
     return L * per_tok
 
 

@@ -85,7 +85,9 @@ def rope_tables(device, theta: float, min_npos: int):
             _rope_retired.append(cur)
         cur = (t, th, npos, ev)
         _rope_tables[key] = cur
-    if not cur[3].query():
+    # (event queries are illegal while a stream is capturing; the eager warm-up that precedes a capture has already
+    # ordered this stream behind the build)
+    if not torch.cuda.is_current_stream_capturing() and not cur[3].query():
         torch.cuda.current_stream(device).wait_event(cur[3])
     return cur[0], cur[1], cur[2]
 

@@ -129,6 +129,11 @@ def fill_layer_cache_gpu(lc, spec: SynthSpec, L: int, seed: int = 0, chunk: int 
         qk.reset(); qv.reset()
         qk.parallel_pack(k.t().contiguous().view(H, 128, T))
         uv, ui, lv, li = qv.topk_thresholds(v)
+        if not lc.sparse_v:
+            # dense-only V (modeling_llama.py:1101-1108): the range is the min / max of the vector, nothing lies beyond it
+            # -> the same packer with those thresholds produces exactly the dense-only codes and LUT rows
+            uv = v.max(dim=-1, keepdim=True).values.expand(-1, uv.shape[1]).contiguous()
+            lv = v.min(dim=-1, keepdim=True).values.expand(-1, lv.shape[1]).contiguous()
         qv.parallel_pack(v.t().contiguous().view(H, 128, T), uv, ui, lv, li)
         sl = slice(done, done + T)
         lc.kcache[:, :, sl] = qk.kcache[:, :, :T]
@@ -136,8 +141,10 @@ def fill_layer_cache_gpu(lc, spec: SynthSpec, L: int, seed: int = 0, chunk: int 
         lc.vlut[sl] = qv.lookup_table[:T]
         lc.vaff[sl, 0] = (uv[:, -1] - lv[:, -1]) / 2
         lc.vaff[sl, 1] = (uv[:, -1] + lv[:, -1]) / 2
-        lc.k_outliers[sl] = qk.outliers[:T]; lc.k_outlier_idx[sl] = qk.outlier_indices[:T]
-        lc.v_outliers[sl] = qv.outliers[:T]; lc.v_outlier_idx[sl] = qv.outlier_indices[:T]
+        if lc.sparse_k:   # (K codes do not depend on the outlier split: outliers are clamped to the LUT ends either way)
+            lc.k_outliers[sl] = qk.outliers[:T]; lc.k_outlier_idx[sl] = qk.outlier_indices[:T]
+        if lc.sparse_v:
+            lc.v_outliers[sl] = qv.outliers[:T]; lc.v_outlier_idx[sl] = qv.outlier_indices[:T]
         done += T
     lc.len = L
     return lc

@@ -501,7 +501,7 @@ class OracleCache:
     QuantK/QuantV.forward_fused_sparse do (ML.py:653-751, 1069-1176)."""
 
     def __init__(self, bits, num_heads, max_len, klut, v_cent, include_sparse=True, sparsity_threshold=0.99,
-                 v_norm=None):
+                 v_norm=None, sparse_v=None):
         """v_norm = (normscale, normoffset) enables Q-Norm on V (ML.py:1054-1066,1115-1118); K Q-Norm is enabled by
         klut['lut2'] (ML.py:485-488): packing uses LUT, dequantisation and outlier subtraction use LUT2."""
         self.bits = bits
@@ -511,6 +511,9 @@ class OracleCache:
         self.klut = klut  # dict from build_k_lut
         self.v_cent = np.sort(np.asarray(v_cent, dtype=np.float32).ravel())
         self.sparse = include_sparse
+        # sparse_v=False with include_sparse=True: capped K outliers only (BASELINE configs[4]); V then takes the
+        # reference's dense-only branch (ML.py:1101-1108, 1178-1201)
+        self.sparse_v = include_sparse if sparse_v is None else (bool(sparse_v) and include_sparse)
         self.n_each = n_out_each(self.hidden, sparsity_threshold)
         W = self.hidden * bits // 32
         self.kwords = np.zeros((W, max_len), dtype=np.int32)
@@ -534,6 +537,7 @@ class OracleCache:
             r = k_outliers_rescaled(k, self.klut["thr_lower"], self.klut["thr_upper"])
             sub = self.klut["lut2"] if self.klut.get("lut2") is not None else lut
             self.k_out[t], self.k_idx[t] = k_outlier_row(k, r, sub, self.n_each)
+        if self.sparse_v:
             hi, lo, ui, li = v_thresholds(v, self.n_each)
             self.vlut[t] = v_token_lut(self.v_cent, hi, lo)
             codes = append_v_codes(v, self.vlut[t], self.bits, lo, hi)
@@ -558,7 +562,7 @@ class OracleCache:
 
     def v_output(self, p):
         o = v_out_dense(p, self.vwords, self.vlut2 if self.v_norm is not None else self.vlut, self.bits, self.len, self.H)
-        if self.sparse:
+        if self.sparse_v:
             o = o + v_out_outliers(p, self.v_out, self.v_idx, self.len, self.H)
         return o
 
@@ -572,7 +576,7 @@ class OracleCache:
 
     def v_recon(self):
         vv = v_dequant(self.vwords[:, :self.len], self.vlut[:self.len], self.bits).astype(np.float64)
-        if self.sparse:
+        if self.sparse_v:
             t = np.broadcast_to(np.arange(self.len)[:, None], self.v_idx[:self.len].shape)
             np.add.at(vv, (self.v_idx[:self.len].astype(np.int64), t), self.v_out[:self.len].astype(np.float64))
         return vv

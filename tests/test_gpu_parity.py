@@ -297,6 +297,36 @@ def test_llama13b_shape_fused_append_and_attend(bits):
     assert rel_err(out, want)[0] < 1e-3
 
 
+@pytest.mark.parametrize("bits,H,mode", [(4, 32, "dense"), (3, 40, "k_only"), (3, 32, "dense"), (4, 32, "k_only")])
+def test_dense_only_and_k_only_outlier_caches(bits, H, mode):
+    """BASELINE configs[3] (no outliers) and configs[4] (capped K outliers only, 13B shape): the fused device append
+    without the V (and K) outlier rows -- the reference's include_sparse=False branches (modeling_llama.py:753-779,
+    1101-1108, 1178-1201) -- is bit-exact against the oracle, and the fused attend over such a cache is within 1e-3."""
+    from kvquant_b200.cache import LayerCache
+    L = 130
+    klut, vcent = quantizer(bits, H=H)
+    sp = spec(H)
+    k, v = sp.k_tokens(L, seed=41), sp.v_tokens(L, seed=42)
+    c = O.OracleCache(bits, H, 192, klut, vcent, include_sparse=(mode != "dense"), sparse_v=False)
+    lc = LayerCache.from_luts(bits, H, 192, klut, vcent, device=DEV, include_sparse=(mode != "dense"), sparse_v=False)
+    assert lc.v_outliers.shape[0] == 1 and (mode == "dense") == (lc.k_outliers.shape[0] == 1)   # no rows allocated
+    for t in range(L):
+        c.append(k[t], v[t])
+        lc.append(cu(k[t]), cu(v[t]))
+    assert np.array_equal(lc.kcache.cpu().numpy().reshape(-1, 192), c.kwords)
+    assert np.array_equal(lc.vcache.cpu().numpy().reshape(-1, 192), c.vwords)
+    assert np.array_equal(lc.vlut.cpu().numpy()[:L], c.vlut[:L])
+    if mode == "k_only":
+        assert np.array_equal(lc.k_outlier_idx.cpu().numpy()[:L], c.k_idx[:L])
+        assert np.array_equal(lc.k_outliers.cpu().numpy()[:L], c.k_out[:L])
+    q = O.rope_rotate_q(sp.q_vec(5), L, 10000.0)
+    _, want = O.attend_ideal(c.k_scores(q), c.v_output)
+    for precision in ("fp16", "fp32"):
+        lc.precision = precision
+        # (130 tokens: the fp16 tables' per-weight noise is not averaged down as at the benchmark lengths)
+        assert rel_err(lc.attend(cu(q)).cpu().numpy(), want)[0] < (1e-3 if precision == "fp32" else 1.5e-3), precision
+
+
 def test_qnorm_2bit_native_path():
     """Q-Norm (reference 2-bit path, modeling_llama.py:485-488, 1115-1118): codes against LUT, dequantisation and
     outlier residuals against LUT2 = (cent*normscale+normoffset)*range+zp."""

@@ -91,7 +91,11 @@ def test_reference_quantk_quantv_run_unmodified_on_the_shim(mods, bits):
     on_shim, on_ref = mods
     sp = spec()
     cal = synth.calibrate(sp, bits, calib_tokens=512, seed=7)
-    T, ND = 96, 64
+    # prefill of 32 tokens: the reference's K prefill packer stages its tables in shared memory without a barrier
+    # (quant_cuda_kernel.cu:1857-1883; 128 threads per block); with more than one warp of tokens its output is not
+    # reproducible run to run (observed on the B200: 256-320 differing values between two identical calls), so a
+    # bit-for-bit comparison against it is only meaningful while one warp owns all the tokens
+    T, ND = 32, 64
     Lmax = 256
     k_all = torch.from_numpy(sp.k_tokens(T + ND, seed=21)).to(DEV)
     v_all = torch.from_numpy(sp.v_tokens(T + ND, seed=22)).to(DEV)
@@ -131,7 +135,7 @@ def test_mirror_classes_equal_the_reference_classes_on_the_shim(mods, bits):
     from kvquant_b200 import cache as kc
     sp = spec()
     cal = synth.calibrate(sp, bits, calib_tokens=512, seed=7)
-    T, ND = 64, 24
+    T, ND = 32, 24
     Lmax = 128
     k_all = torch.from_numpy(sp.k_tokens(T + ND, seed=31)).to(DEV).half().float()
     v_all = torch.from_numpy(sp.v_tokens(T + ND, seed=32)).to(DEV).half().float()
