@@ -35,11 +35,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (model, bits, L (quantised slots), n_sink, description = BASELINE.json configs[i])
-    "7b-3b-128k": ("7b", 3, 131072, 5, "LLaMA-7B 3b NUQ + 1% outliers + 5 fp16 sink tokens, seqlen 128K, 1xB200 (configs[2])"),
-    "7b-4b-128k": ("7b", 4, 131072, 0, "LLaMA-7B 4b NUQ + 1% outliers, seqlen 128K (north_star roofline target)"),
-    "7b-4b-32k": ("7b", 4, 32768, 0, "LLaMA-7B 4b NUQ + 1% outliers, seqlen 32K, 1xB200 decode (configs[1])"),
-    "7b-4b-4k": ("7b", 4, 4096, 0, "single-node smoke size"),
+    # name: (model, bits, L (quantised slots), n_sink, outliers, description = BASELINE.json configs[i])
+    #   outliers: "kv" = 1 % dense-and-sparse on K and V, "k" = capped K outliers only, "none" = dense-only
+    "7b-3b-128k": ("7b", 3, 131072, 5, "kv", "LLaMA-7B 3b NUQ + 1% outliers + 5 fp16 sink tokens, seqlen 128K, 1xB200 (configs[2])"),
+    "7b-4b-128k": ("7b", 4, 131072, 0, "kv", "LLaMA-7B 4b NUQ + 1% outliers, seqlen 128K (north_star roofline target)"),
+    "7b-4b-32k": ("7b", 4, 32768, 0, "kv", "LLaMA-7B 4b NUQ + 1% outliers, seqlen 32K, 1xB200 decode (configs[1])"),
+    "7b-4b-4k": ("7b", 4, 4096, 0, "kv", "single-node smoke size"),
+    "7b-4b-1m": ("7b", 4, 1048576, 0, "none", "LLaMA-7B 4b NUQ, seqlen 1M, layer-pipeline across 4xB200 (configs[3])"),
+    "13b-3b-1m": ("13b", 3, 1048576, 0, "k", "LLaMA-13B 3b NUQ + capped-K outliers, seqlen 1M, layer-pipeline across 8xB200 (configs[4])"),
 }
 DEFAULT_WORKLOAD = "7b-3b-128k"   # BASELINE.json's metric is quoted at seqlen 128K; this config fits one GPU
 
@@ -112,39 +115,175 @@ def build_quantizer(cfg_bits, H, device):
 
 
 # ------------------------------------------------------------------------------------------------------------
-# reference arm: CPU port of the path on the host cores, bounded sample
+# reference arm / cpu_baseline: CPU port of the path on the host cores, fixed bounded sample, no GPU involved
 # ------------------------------------------------------------------------------------------------------------
-def cpu_baseline_run(layer_arrays, bits, H, Lmax, L, n_out, n_layers, theta, pos_offset, budget_s=12.0):
-    """Time the C port's attend for one layer over a token sample sized to ~budget_s of CPU work; extrapolate to
-    tokens/sec of the whole model's attention (n_layers x L tokens; the dense GEMVs are NOT added, which only
-    favours the CPU number).  Returns (tokens_per_sec, cores, sample description)."""
+CPU_SAMPLE_TOKENS = 32768      # tokens of ONE layer per timed call (fixed: the same work on every box and every run)
+
+
+def host_cores():
+    """(usable cores, description): scheduler affinity and the cgroup CPU quota, whichever is smaller."""
+    n_aff = len(os.sched_getaffinity(0))
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            a, b = f.read().split()[:2]
+            if a != "max":
+                quota = float(a) / float(b)
+    except (OSError, ValueError):
+        pass
+    n = n_aff if quota is None else max(1, min(n_aff, int(quota)))
+    return n, "affinity %d cores, cgroup cpu quota %s" % (n_aff, "none" if quota is None else "%.1f cores" % quota)
+
+
+def synth_host_layer(bits, H, Ls, n_out, sparse_k, sparse_v, seed=0):
+    """One layer's quantised cache of Ls tokens generated ON THE HOST (numpy): uniformly random codes, a calibrated
+    K LUT, per-token V LUT rows, sorted distinct outlier indices with heavy-tailed values.  The C port's run time does
+    not depend on the code values (same loads, same arithmetic), so this times exactly the work of a real cache."""
+    import numpy as np
+    from kvquant_b200 import synth
+    rng = np.random.default_rng(seed)
+    hidden = H * 128
+    W = hidden * bits // 32
+    Lmax = Ls + 64
+    sp = synth.SynthSpec(H, 128, seed=0)
+    cal = synth.calibrate(sp, bits, calib_tokens=256, seed=7)
+    up = cal["k"][0].astype(np.float16).astype(np.float32)
+    lo = cal["k"][1].astype(np.float16).astype(np.float32)
+    cent = np.sort(cal["k"][2][0].ravel().astype(np.float32))
+    klut = (cent[None, :] * ((up - lo) / 2)[:, None] + ((up + lo) / 2)[:, None]).astype(np.float32)
+    vcent = np.sort(cal["v"][2][0].ravel().astype(np.float32))
+    sf = np.exp(rng.normal(0, 0.3, (Lmax, 1))).astype(np.float32) * 2.5
+    vlut = (vcent[None, :] * sf + rng.normal(0, 0.05, (Lmax, 1)).astype(np.float32)).astype(np.float32)
+    a = dict(kcache=rng.integers(0, 2 ** 32, (W, Lmax), dtype=np.uint32).view(np.int32),
+             vcache=rng.integers(0, 2 ** 32, (W, Lmax), dtype=np.uint32).view(np.int32),
+             klut=np.ascontiguousarray(klut), vlut=np.ascontiguousarray(vlut), q=sp.q_vec(1), Lmax=Lmax)
+
+    def rows():
+        idx = np.sort(np.argsort(rng.random((Lmax, hidden)), axis=1)[:, :n_out], axis=1).astype(np.int32)
+        val = rng.standard_t(3, (Lmax, n_out)).astype(np.float32) * 3
+        return np.ascontiguousarray(val), np.ascontiguousarray(idx)
+    a["k_out"], a["k_idx"] = rows() if sparse_k else (None, None)
+    a["v_out"], a["v_idx"] = rows() if sparse_v else (None, None)
+    return a
+
+
+def cpu_baseline_run(bits, H, L, n_out, sparse_k, sparse_v, n_layers, theta, pos_offset, repeats=5, arrays=None):
+    """Time the C port's attend (oracle/kvq_oracle_port.c, OpenMP on every usable host core) for one layer over a FIXED
+    sample of CPU_SAMPLE_TOKENS tokens, `repeats` times; the best time is extrapolated to tokens/sec of the whole
+    model's attention (n_layers x L tokens; the dense GEMVs are NOT added, which only favours the CPU number).
+    Returns (tokens_per_sec, cores, sample description, per-call seconds list, arrays)."""
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import build_oracle_c
     lib = build_oracle_c.load()
-    lib.kvq_port_set_threads(len(os.sched_getaffinity(0)))   # not OMP_NUM_THREADS (torchrun sets it to 1)
+    cores, cores_desc = host_cores()
+    lib.kvq_port_set_threads(cores)        # not OMP_NUM_THREADS (torchrun sets it to 1)
     cores = lib.kvq_port_threads()
-    a = layer_arrays
+    Ls = min(L, CPU_SAMPLE_TOKENS)
+    a = arrays if arrays is not None else synth_host_layer(bits, H, Ls, n_out, sparse_k, sparse_v)
     q = np.ascontiguousarray(a["q"], dtype=np.float32)
     out = np.zeros((H, 128), np.float32)
+    scratch = np.zeros((H, Ls), np.float32)
 
-    def run(Ls):
-        scratch = np.zeros((H, Ls), np.float32)
+    def ptr(x):
+        return x.ctypes.data if x is not None else None
+    # the port takes one outlier width: rows of a dense-only side are simply absent (NULL)
+    times = []
+    for _ in range(repeats + 1):
         t0 = time.perf_counter()
-        lib.kvq_port_attend(bits, q.ctypes.data, a["kcache"].ctypes.data, a["klut"].ctypes.data,
-                            a["k_out"].ctypes.data, a["k_idx"].ctypes.data, a["vcache"].ctypes.data,
-                            a["vlut"].ctypes.data, a["v_out"].ctypes.data, a["v_idx"].ctypes.data, n_out, H, Lmax, Ls,
-                            theta, pos_offset, out.ctypes.data, scratch.ctypes.data)
-        return time.perf_counter() - t0
+        lib.kvq_port_attend(bits, q.ctypes.data, a["kcache"].ctypes.data, a["klut"].ctypes.data, ptr(a["k_out"]),
+                            ptr(a["k_idx"]), a["vcache"].ctypes.data, a["vlut"].ctypes.data, ptr(a["v_out"]),
+                            ptr(a["v_idx"]), n_out, H, a["Lmax"], Ls, theta, pos_offset, out.ctypes.data,
+                            scratch.ctypes.data)
+        times.append(time.perf_counter() - t0)
+    times = times[1:]                      # first call: page faults / thread start-up
+    best = min(times)
+    tok_s = 1.0 / (best * (L / Ls) * n_layers)
+    desc = ("C port (oracle/kvq_oracle_port.c, OpenMP, %d threads; %s) of one layer's attend over a fixed %d of %d "
+            "tokens of a host-generated cache, best of %d calls (%.1f..%.1f ms), extrapolated to %d layers x %d tokens; "
+            "GEMVs excluded" % (cores, cores_desc, Ls, L, len(times), 1e3 * best, 1e3 * max(times), n_layers, L))
+    return tok_s, cores, desc, times, a
 
-    t_probe = run(min(L, 2048))
-    per_tok = t_probe / min(L, 2048)
-    Ls = int(max(2048, min(L, budget_s / 3 / per_tok)))
-    ts = sorted(run(Ls) for _ in range(3))
-    t_layer_full = ts[1] * (L / Ls)
-    tok_s = 1.0 / (t_layer_full * n_layers)
-    return tok_s, cores, "C port (oracle/kvq_oracle_port.c, OpenMP) of one layer's attend over %d of %d tokens, median of 3, " \
-        "extrapolated to %d layers x %d tokens; GEMVs excluded" % (Ls, L, n_layers, L)
+
+def _time_cuda(fn, iters, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def reference_cuda_anchor(lc, cfg, L, n_sink, bits, ms_ours, peak):
+    """The kernel-vs-kernel anchor: the reference's OWN CUDA kernels (oracle/_ref/quant_cuda_ref.so =
+    deployment/kvquant/quant_cuda_kernel.cu compiled unmodified for sm_100a by oracle/build_ref.py) on this GPU, on one
+    layer's cache of this workload: its K op (dense + SPMV_ATOMIC_ROPE_BALANCED) and V op (dense + SPMV_ATOMIC_BALANCED)
+    -- the two launches of the chain modeling_llama.py:1963-1999, without its torch glue -- next to our fused attend."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import build_ref
+        ref = build_ref.load()
+    except Exception as e:  # noqa: BLE001
+        ref = None
+        why = repr(e)[:120]
+    if ref is None:
+        return {"unavailable": "oracle/_ref/quant_cuda_ref.so not present (%s)" % (locals().get("why", "not built"))}
+    if not (lc.sparse_k and lc.sparse_v):
+        return {"unavailable": "the reference has no mixed / dense-only fused op chain to time for this workload"}
+    H, dev = cfg.n_heads, lc.device
+    q1 = torch.randn((1, H, 128), device=dev).half().float()
+    mulK = torch.zeros((1, H, L), device=dev)
+    pV = torch.softmax(torch.randn((1, H, L), device=dev), -1)
+    mulV = torch.zeros((1, H, 128), device=dev)
+    kop = getattr(ref, "vecquant%dmatmul_nuq_perchannel_transposed_rope_mha_batched_fused_opt2" % bits)
+    vop = getattr(ref, "vecquant%dmatmul_nuq_perchannel_transposed_mha_batched_fused_opt2" % bits)
+    lutK = lc.klut.view(H, 128, -1)
+    ms_k = _time_cuda(lambda: kop(q1, lc.kcache, mulK, lutK, L, lc.k_outliers, lc.k_outlier_idx, cfg.rope_theta, n_sink), 5)
+    ms_v = _time_cuda(lambda: vop(pV, lc.vcache, mulV, lc.vlut, L, lc.v_outliers, lc.v_outlier_idx), 5)
+    nbytes = L * lc.bytes_per_token()
+    chain = ms_k + ms_v
+    return {"k_op_ms": ms_k, "v_op_ms": ms_v, "chain_ms": chain, "gbs": nbytes / chain / 1e6,
+            "frac": nbytes / chain / 1e6 / peak, "ours_ms": ms_ours, "speedup": chain / ms_ours,
+            "what": "reference quant_cuda kernels (unmodified, sm_100a) on one layer of this workload, same GPU, same cache"}
+
+
+def north_star_anchor(dev, cfg7b_like, peak, L=131072, n_caches=3):
+    """north_star's roofline kernel: the fused 4-bit NUQ dequant + sparse attend matvec at seqlen 128K (7B shapes,
+    1 % outliers), timed with CUDA events while cycling over `n_caches` distinct layer caches (1.8 GB: nothing stays
+    in L2), whatever workload this bench run is on."""
+    import torch
+    from kvquant_b200 import synth
+    from kvquant_b200.cache import LayerCache
+    H = 32
+    sp, quantizer = build_quantizer(4, H, dev)
+    caches = []
+    for i in range(n_caches):
+        lc = LayerCache.from_luts(4, H, L + 64, quantizer["klut"], quantizer["v_cent"], device=dev)
+        synth.fill_layer_cache_gpu(lc, sp, L, seed=900 + i)
+        caches.append(lc)
+    q = torch.randn((H, 128), device=dev).half().float()
+    out = {}
+    for prec in ("fp16", "fp32"):
+        for lc in caches:
+            lc.precision = prec
+
+        def run():
+            for lc in caches:
+                lc.attend(q)
+        ms = _time_cuda(run, 10) / n_caches
+        nbytes = L * caches[0].bytes_per_token()
+        out[prec] = {"ms": ms, "gbs": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / peak}
+    rec = dict(out["fp16"], workload="7b-4b-128k", algorithmic_bytes_per_launch=L * caches[0].bytes_per_token(),
+               table_precision="fp16", exact_fp32_tables=out["fp32"])
+    del caches
+    torch.cuda.empty_cache()
+    return rec
 
 
 def ncu_traffic(bits, L):
@@ -169,6 +308,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-anchors", action="store_true",
+                    help="skip the two extra roofline records (reference CUDA kernels on this GPU, 4-bit 128K attend)")
     ap.add_argument("--parallelism", default="auto", choices=["auto", "pp", "sp"],
                     help="N>1: pp = layer-group pipeline (the reference's scheme, north_star: buys capacity, not "
                          "tokens/sec at batch 1); sp = sequence-sharded attention with replicated weights (SURVEY 8e-2 / "
@@ -191,8 +332,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    model, bits, L, n_sink, desc = WORKLOADS[args.workload]
-    metric = "decode tokens/sec @ seqlen %dK (LLaMA-7B, bs1)" % (L // 1024)
+    model, bits, L, n_sink, outl, desc = WORKLOADS[args.workload]
+    metric = "decode tokens/sec @ seqlen %dK (LLaMA-%s, bs1)" % (L // 1024, model.upper())
     base = {"metric": metric, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (random-init fp16 LLaMA-7B weights, synthetic K/V packed by the real prefill packers)"}
@@ -200,8 +341,10 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+        dev = torch.device("cpu")        # the reference arm never touches a GPU
+    else:
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
     if world > 1 and args.impl == "ours":
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -218,10 +361,13 @@ def main():
     L_local = L // world if sp_mode else L
     # room for every step this run appends (warm-up + profile + timed, device and e2e loops)
     headroom = (2 * (args.steps + args.warmup) + 3 + 8 + 63) // 64 * 64
-    cfg = kd.DecodeConfig.llama7b(bits=bits, n_sink=n_sink, max_len=L_local + headroom)
-    sp, quantizer = build_quantizer(bits, cfg.n_heads, dev)
+    mk = kd.DecodeConfig.llama13b if model == "13b" else kd.DecodeConfig.llama7b
+    cfg = mk(bits=bits, n_sink=n_sink, max_len=L_local + headroom, include_sparse=(outl != "none"),
+             sparse_v=(outl == "kv"))
+    sp, quantizer = (None, None) if args.impl == "reference" else build_quantizer(bits, cfg.n_heads, dev)
     config = {"workload": args.workload, "description": desc, "bits": bits, "seq_len": L + n_sink, "n_sink": n_sink,
-              "outliers": "1% (21+21 per token per cache)", "layers": cfg.n_layers, "parallelism": par_label,
+              "outliers": {"kv": "1% (n_each + n_each per token per cache)", "k": "capped 1% on K only", "none": "none (dense-only)"}[outl],
+              "layers": cfg.n_layers, "parallelism": par_label,
               "l2_policy": "inputs larger than L2: every step streams all layers' caches (>= 4 GB) and 13.5 GB of weights",
               "step": ("one CUDA-graph replay = the next decode step of a growing cache (length and position live in "
                        "device memory; step i appends slot L+i and attends over L+i+1 slots)") if args.graph == "dynamic"
@@ -229,26 +375,18 @@ def main():
 
     # ---------------------------------------------------------------------------------------------------------
     if args.impl == "reference":
-        # build ONE layer's cache on the GPU (real packers), bring it to the host, time the CPU port
-        from kvquant_b200.cache import LayerCache
-        lc = LayerCache.from_luts(bits, cfg.n_heads, cfg.max_len, quantizer["klut"], quantizer["v_cent"], device=dev)
-        synth.fill_layer_cache_gpu(lc, sp, L, seed=0)
-        arrs = dict(kcache=lc.kcache.cpu().numpy(), vcache=lc.vcache.cpu().numpy(), klut=lc.klut.cpu().numpy(),
-                    vlut=lc.vlut.cpu().numpy(), k_out=lc.k_outliers.cpu().numpy(), k_idx=lc.k_outlier_idx.cpu().numpy(),
-                    v_out=lc.v_outliers.cpu().numpy(), v_idx=lc.v_outlier_idx.cpu().numpy(), q=sp.q_vec(1))
-        vals = []
-        info = None
-        # each step is a bounded sample; the whole --steps/--warmup run stays within ~2.5 minutes of CPU time
-        ref_budget = max(1.5, min(6.0, 150.0 / max(1, args.warmup + args.steps)))
-        for i in range(args.warmup + args.steps):
-            tok_s, cores, sample = cpu_baseline_run(arrs, bits, cfg.n_heads, cfg.max_len, L, lc.n_out, cfg.n_layers,
-                                                    cfg.rope_theta, n_sink, budget_s=ref_budget)
-            if i >= args.warmup:
-                vals.append(tok_s)
-            info = (cores, sample)
-        v = float(np.median(vals))
+        # GPU-free: host-generated cache, fixed sample; one "step" = one timed call of the C port
+        n_out = 2 * (int(((1 - 0.99) / 2) * cfg.hidden) + 1)
+        tok_s, cores, sample, times, _ = cpu_baseline_run(bits, cfg.n_heads, L, n_out, outl != "none", outl == "kv",
+                                                          cfg.n_layers, cfg.rope_theta, n_sink,
+                                                          repeats=args.warmup + args.steps)
+        timed = times[args.warmup:] if len(times) > args.warmup else times
+        Ls = min(L, CPU_SAMPLE_TOKENS)
+        vals = sorted(1.0 / (t * (L / Ls) * cfg.n_layers) for t in timed)
+        v = vals[-1]                     # best call: the least disturbed one (the host cores are shared)
         line = dict(base, impl="reference", value=v, ms_per_step=1000.0 / v, config=config, gpu_launches=0,
-                    cpu_baseline={"value": v, "unit": "tokens/s", "cores": info[0], "kind": "port", "sample": info[1]},
+                    cpu_baseline={"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample,
+                                  "median": vals[len(vals) // 2], "worst": vals[0]},
                     e2e={"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                     clocks=None, roofline=None)
         print(json.dumps(line), flush=True)
@@ -275,28 +413,22 @@ def main():
     t_fill = time.time() - t_fill
 
     n0 = _lib.launch_count()
+    pp_mode = world > 1 and not sp_mode
     gs = kd.GraphedStage(stage, L_local, first=(rank == 0 or sp_mode), last_to_logits=(world == 1 or sp_mode),
-                         dynamic=(args.graph == "dynamic"), pos=(n_sink + L) if sp_mode else None)
-    launches_per_step = (_lib.launch_count() - n0) // (5 if sp_mode else 3)   # eager warm-up passes + 1 capture pass
-    if world > 1 and rank == 0:
-        head_graph_in = torch.zeros(cfg.hidden, dtype=torch.float16, device=dev)
+                         dynamic=(args.graph == "dynamic"), pos=(n_sink + L) if sp_mode else None,
+                         pp=(rank, world) if pp_mode else None)
+    launches_per_step = (_lib.launch_count() - n0) // (5 if (sp_mode or pp_mode) else 3)   # eager warm-up passes + 1 capture pass
     pinned_tok = torch.zeros(1, dtype=torch.long).pin_memory()
     pinned_logits = torch.zeros(cfg.vocab, dtype=torch.float16).pin_memory()
     logits_dev = [None]
 
     def step_device():
         """one decode step, inputs resident on the device"""
-        if world == 1 or sp_mode:
-            gs.replay()
-            logits_dev[0] = gs.logits
-            return
-        if rank > 0:
-            dist.recv(gs.x_in, src=rank - 1)
+        # pp: the hops are NCCL send/recv kernels inside the captured graphs (rank 0 replays two: its layers, then
+        # recv + norm + lm_head)
         gs.replay()
-        dist.send(gs.y, dst=(rank + 1) % world)
-        if rank == 0:
-            dist.recv(head_graph_in, src=world - 1)
-            logits_dev[0] = stage.head(head_graph_in)
+        if rank == 0 or sp_mode:
+            logits_dev[0] = gs.logits
 
     def step_e2e(i):
         """same step through host buffers: token id H2D from pinned memory, logits D2H to pinned memory"""
@@ -352,65 +484,77 @@ def main():
     # ---- roofline of the dominant op (fused attend), measured live on this stream, cycling over the layers -------
     roof = None
     cpu_b = None
+    layers = stage.layers
+    q = torch.randn((cfg.n_heads, 128), device=dev).half().float()
+    reps = max(2, 64 // len(layers))
+
+    def time_loop(fn):
+        for ly in layers[:2]:
+            fn(ly)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            for ly in layers:
+                fn(ly)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / (reps * len(layers))
+
+    Lq = layers[0].cache.len      # current length (the timed steps appended to the cache)
+    # every rank times the fused attend of ITS layers (pp: one record per pipeline stage; sp: per sequence shard)
+    ms_att = time_loop(lambda ly: ly.cache.attend(q, rope_theta=cfg.rope_theta))
+    ms_all = torch.tensor([ms_att], device=dev)
+    if world > 1:
+        gath = [torch.zeros(1, device=dev) for _ in range(world)]
+        dist.all_gather(gath, ms_all)
+        ms_all = torch.cat(gath)
     if rank == 0:
         peak, peak_src = measured_peak()
-        layers = stage.layers
-        q = torch.randn((cfg.n_heads, 128), device=dev).half().float()
-        reps = max(2, 64 // len(layers))
-
-        def time_loop(fn):
-            for ly in layers[:2]:
-                fn(ly)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(reps):
-                for ly in layers:
-                    fn(ly)
-            b.record()
-            torch.cuda.synchronize()
-            return a.elapsed_time(b) / (reps * len(layers))
-
-        Lq = layers[0].cache.len      # current length (the timed steps appended to the cache)
-        ms_att = time_loop(lambda ly: ly.cache.attend(q, rope_theta=cfg.rope_theta))
-        from kvquant_b200 import quant_cuda as qc
-        mulK = torch.zeros((1, cfg.n_heads, Lq), device=dev)
-        pV = torch.softmax(torch.randn((1, cfg.n_heads, Lq), device=dev), -1)
-        mulV = torch.zeros((1, cfg.n_heads, 128), device=dev)
-        q1 = q[None].contiguous()
-        kop = getattr(qc, "vecquant%dmatmul_nuq_perchannel_transposed_rope_mha_batched_fused_opt2" % bits)
-        vop = getattr(qc, "vecquant%dmatmul_nuq_perchannel_transposed_mha_batched_fused_opt2" % bits)
-        ms_k = time_loop(lambda ly: kop(q1, ly.cache.kcache, mulK, ly.cache.klut.view(cfg.n_heads, 128, -1), Lq,
-                                        ly.cache.k_outliers, ly.cache.k_outlier_idx, cfg.rope_theta, n_sink))
-        ms_v = time_loop(lambda ly: vop(pV, ly.cache.vcache, mulV, ly.cache.vlut, Lq, ly.cache.v_outliers,
-                                        ly.cache.v_outlier_idx))
         n_out = layers[0].cache.n_out
         b_att = kd.layer_step_bytes(cfg, Lq)
-        b_k = Lq * (cfg.hidden * bits // 8 + 8 * n_out)
-        b_v = Lq * (cfg.hidden * bits // 8 + 8 * n_out + 4 * 2 ** bits)
+        per_kernel = None
+        if outl == "kv":       # the legacy two-op surface (what the reference's QuantK / QuantV call), timed separately
+            from kvquant_b200 import quant_cuda as qc
+            mulK = torch.zeros((1, cfg.n_heads, Lq), device=dev)
+            pV = torch.softmax(torch.randn((1, cfg.n_heads, Lq), device=dev), -1)
+            mulV = torch.zeros((1, cfg.n_heads, 128), device=dev)
+            q1 = q[None].contiguous()
+            kop = getattr(qc, "vecquant%dmatmul_nuq_perchannel_transposed_rope_mha_batched_fused_opt2" % bits)
+            vop = getattr(qc, "vecquant%dmatmul_nuq_perchannel_transposed_mha_batched_fused_opt2" % bits)
+            ms_k = time_loop(lambda ly: kop(q1, ly.cache.kcache, mulK, ly.cache.klut.view(cfg.n_heads, 128, -1), Lq,
+                                            ly.cache.k_outliers, ly.cache.k_outlier_idx, cfg.rope_theta, n_sink))
+            ms_v = time_loop(lambda ly: vop(pV, ly.cache.vcache, mulV, ly.cache.vlut, Lq, ly.cache.v_outliers,
+                                            ly.cache.v_outlier_idx))
+            b_k = Lq * (cfg.hidden * bits // 8 + 8 * n_out)
+            b_v = Lq * (cfg.hidden * bits // 8 + 8 * n_out + 4 * 2 ** bits)
+            per_kernel = {"legacy_k_op": {"ms": ms_k, "bytes": b_k, "gbs": b_k / ms_k / 1e6, "frac": b_k / ms_k / 1e6 / peak},
+                          "legacy_v_op": {"ms": ms_v, "bytes": b_v, "gbs": b_v / ms_v / 1e6, "frac": b_v / ms_v / 1e6 / peak}}
+            del mulK, pV
         ach = b_att / ms_att / 1e6
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": ncu_traffic(bits, Lq),
                 "peak_source": peak_src,
                 "kernel": "kvq_attend = attend_init + k_outlier_pers + k_scores(3) + v_native + attend_combine",
                 "algorithmic_bytes_per_launch": b_att, "ms_per_launch": ms_att,
-                "per_kernel": {"k_scores_kernel": {"ms": ms_k, "bytes": b_k, "gbs": b_k / ms_k / 1e6, "frac": b_k / ms_k / 1e6 / peak},
-                               "v_accum_kernel": {"ms": ms_v, "bytes": b_v, "gbs": b_v / ms_v / 1e6, "frac": b_v / ms_v / 1e6 / peak}},
+                "per_kernel": per_kernel,
+                "per_rank": [{"rank": r, "ms_per_launch": float(m), "gbs": b_att / float(m) / 1e6,
+                              "frac": b_att / float(m) / 1e6 / peak} for r, m in enumerate(ms_all.tolist())],
                 "attend_share_of_step": ms_att * len(layers) / ms_step}
+        roof["kernel"] = ("kvq_attend (table precision %s) = attend_init + k_fast_prep + [memset + k_outlier_pers] + "
+                          "k_fast (fp32: k_scores / k_scores3) + v_native + attend_combine" % layers[0].cache.precision)
+        if not args.no_anchors:
+            roof["reference_cuda"] = reference_cuda_anchor(layers[0].cache, cfg, Lq, n_sink, bits, ms_att, peak)
+            roof["north_star_kernel"] = north_star_anchor(dev, cfg, peak)
         if not args.no_cpu_baseline:
-            lc = layers[0].cache
-            arrs = dict(kcache=lc.kcache.cpu().numpy(), vcache=lc.vcache.cpu().numpy(), klut=lc.klut.cpu().numpy(),
-                        vlut=lc.vlut.cpu().numpy(), k_out=lc.k_outliers.cpu().numpy(), k_idx=lc.k_outlier_idx.cpu().numpy(),
-                        v_out=lc.v_outliers.cpu().numpy(), v_idx=lc.v_outlier_idx.cpu().numpy(), q=q.cpu().numpy())
-            tok_s, cores, sample = cpu_baseline_run(arrs, bits, cfg.n_heads, cfg.max_len, L_local, n_out,
-                                                    cfg.n_layers * (world if sp_mode else 1), cfg.rope_theta, n_sink,
-                                                    budget_s=15.0)
+            tok_s, cores, sample, _, _ = cpu_baseline_run(bits, cfg.n_heads, L, n_out, outl != "none", outl == "kv",
+                                                          cfg.n_layers, cfg.rope_theta, n_sink, repeats=5)
             cpu_b = {"value": tok_s, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
-        config.update(cache_fill_s=round(t_fill, 1), weight_bytes=stage.weight_bytes(),
-                      cache_bytes_per_layer=kd.layer_step_bytes(cfg, L))
-        line = dict(base, value=value, ms_per_step=ms_step, config=config, clocks=clocks,
+        setup = dict(cache_fill_s=round(t_fill, 1), weight_bytes=stage.weight_bytes(),
+                     cache_bytes_per_layer=kd.layer_step_bytes(cfg, L), table_precision=stage.layers[0].cache.precision)
+        line = dict(base, value=value, ms_per_step=ms_step, config=config, setup=setup, clocks=clocks,
                     e2e={"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": 8,
                          "d2h_bytes_per_step": cfg.vocab * 2},
                     gpu_launches=int(launches_per_step * args.steps), roofline=roof, cpu_baseline=cpu_b)

@@ -765,8 +765,9 @@ int k_scores_fused(int bits, const float* q, const int32_t* cache, float* scores
   return k_scores_dispatch(bits, p, st);
 }
 
-// fp16 mode of the fused attend (rope_half != null): outlier scatter straight into the head-major score buffer
-// (cleared first), then the fp16-table dense kernel folds it in: out = (partial + S) * scale.
+// K side of the fused attend: outlier scatter straight into the head-major score buffer (cleared first), then the
+// TMA-fed dense kernel folds it in: out = (partial + S) * scale.  rope_half == null: exact fp32 ratio form
+// (kvq_kratio.cu); otherwise the fp16-table form (kvq_kfast.cu).
 int k_scores_fused_fast(int bits, const float* q, const int32_t* cache, float* scores, int64_t score_stride,
                         const float* lut, const float* outliers, const int32_t* outlier_idx, int n_out, int H,
                         int64_t Lmax, int64_t L, const float* rope, const void* rope_half, int64_t rope_npos,
@@ -784,6 +785,9 @@ int k_scores_fused_fast(int bits, const float* q, const int32_t* cache, float* s
     if (rc != 0) return rc;
     accumulate = 1;
   }
+  if (rope_half == nullptr)   // exact mode: fp32 ratio form (kvq_kratio.cu)
+    return k_ratio_dispatch(bits, q, cache, scores, score_stride, lut, H, Lmax, L, rope, rope_npos, pos_offset, gmax, scale,
+                            accumulate, len_dev, len_add, qtab, st);
   return k_fast_dispatch(bits, q, cache, scores, score_stride, lut, H, Lmax, L, rope_half, rope_npos, pos_offset, gmax,
                          scale, accumulate, len_dev, len_add, qtab, st);
 }

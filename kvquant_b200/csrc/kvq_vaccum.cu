@@ -527,6 +527,13 @@ int k_scores_fused_fast(int bits, const float* q, const int32_t* cache, float* s
                         int64_t Lmax, int64_t L, const float* rope, const void* rope_half, int64_t rope_npos,
                         int pos_offset, float* gmax, float scale, const int64_t* len_dev, int64_t len_add, void* qtab,
                         cudaStream_t st);
+// KVQ_K_IMPL set (generic / pair / kappa / lds64): round 1's 8-byte-entry kernels serve the exact mode of the fused attend
+static int k_legacy_fused() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("KVQ_K_IMPL"); v = (e && e[0]) ? 1 : 0; }
+  return v;
+}
+
 static int check_v_common(int H, int64_t Lmax, int64_t L, const void* cache) {
   if (H <= 0 || (H & 3) != 0 || H > 64 || L < 0 || L > Lmax) return KVQ_E_SHAPE;
   if ((Lmax & 3) != 0 || (reinterpret_cast<uintptr_t>(cache) & 15) != 0) return KVQ_E_ALIGN;
@@ -570,9 +577,9 @@ static const int kMaxPart = 256;
 
 int64_t kvq_attend_scratch_bytes(int H, int64_t L) {
   // scores [H][L'] + gmax [H] + sink scores [H][64] + partial o / l of <= kMaxPart CTAs + token-major K-outlier
-  // partials [L'][H'] (H' = H rounded up to 32) + the premultiplied half2 K table [H][128][16] of the fp16 mode
+  // partials [L'][H'] (H' = H rounded up to 32) + the premultiplied K table [H][128][16] and ratios [H][128]
   return 4 * ((int64_t)H * round_up(L, 32) + H + (int64_t)H * 64 + (int64_t)kMaxPart * H * kHeadDim + (int64_t)kMaxPart * H +
-              round_up(L, 32) * round_up(H, 32) + (int64_t)H * kHeadDim * 16) + 256;
+              round_up(L, 32) * round_up(H, 32) + (int64_t)H * kHeadDim * 17) + 256;
 }
 
 }  // extern "C"
@@ -609,12 +616,14 @@ static int attend_impl(int bits, const float* q, const int32_t* kcache, const fl
   KVQ_LAUNCH_CHECK();
   int n_cta = 0;
   if (L > 0) {
-    if (fast)
-      rc = k_scores_fused_fast(bits, q, kcache, scores, stride, klut, k_outliers, k_outlier_idx, n_out, H, Lmax, L,
-                               rope_cos_sin, rope_half, rope_npos, pos_offset, gmax, scale, len_dev, len_add, qtab, st);
-    else
+    // KVQ_K_IMPL (generic / pair / kappa) keeps round 1's LDS.64 kernels reachable for A/B runs; otherwise the
+    // TMA-fed kernels: exact fp32 ratio form, or (rope_half given) the fp16-table form
+    if (!fast && k_legacy_fused())
       rc = k_scores_fused(bits, q, kcache, scores, stride, klut, k_outliers, k_outlier_idx, n_out, H, Lmax, L,
                           rope_cos_sin, rope_npos, theta, pos_offset, gmax, scale, len_dev, len_add, opart, opart_stride, st);
+    else
+      rc = k_scores_fused_fast(bits, q, kcache, scores, stride, klut, k_outliers, k_outlier_idx, n_out, H, Lmax, L,
+                               rope_cos_sin, rope_half, rope_npos, pos_offset, gmax, scale, len_dev, len_add, qtab, st);
     if (rc) return rc;
     rc = KVQ_E_UNSUPPORTED;
     if (native_v)

@@ -278,8 +278,14 @@ class GraphedStage:
     every replay of the SAME graph is the next decode step of a growing cache (slot L, L+1, ...)."""
 
     def __init__(self, stage: DecoderStage, L: int, first: bool, last_to_logits: bool, dynamic: bool = False,
-                 pos: int = None):
+                 pos: int = None, pp=None):
+        """pp = (rank, world): layer-group pipeline (the reference's multi-GPU scheme, modeling_llama.py:2428-2453, 2552-2585).
+        The hop of the [hidden] fp16 vector is PART of the captured step: rank r's graph is
+        `recv from r-1 -> its layers -> send to (r+1) % world`, rank 0 additionally owns a second graph
+        `recv from world-1 -> norm + lm_head`.  NCCL send/recv kernels inside the graph cost microseconds per hop; issued
+        from the host (round 1) every hop paid ~0.8 ms of launch latency and the pipeline ran slower than one GPU."""
         self.stage = stage
+        self.pp = pp
         dev = stage.device
         cfg = stage.cfg
         self.tok = torch.zeros(1, dtype=torch.long, device=dev)
@@ -291,12 +297,36 @@ class GraphedStage:
         if dynamic:
             stage.enable_device_length(L, self.pos0)
 
+        self.head_in = None
+        self.head_graph = None
+        if pp is not None and pp[1] > 1:
+            import torch.distributed as dist
+            prank, pworld = pp
+            if prank == 0:
+                self.head_in = torch.zeros(cfg.hidden, dtype=torch.float16, device=dev)
+
         def body():
+            if pp is not None and pp[1] > 1 and pp[0] > 0:
+                dist.recv(self.x_in, src=pp[0] - 1)
             x = stage.embed_token(self.tok) if first else self.x_in
             if not dynamic:
                 stage.set_len(L)
             y = stage.forward(x)
+            if pp is not None and pp[1] > 1:
+                dist.send(y, dst=(pp[0] + 1) % pp[1])
             return y
+
+        def head_body():     # rank 0 of a pipeline: the last stage's output comes back for norm + lm_head
+            dist.recv(self.head_in, src=pp[1] - 1)
+            return stage.head(self.head_in)
+
+        if pp is not None and pp[1] > 1:   # eager pipeline steps first: NCCL creates its P2P channels on first use
+            for _ in range(2):
+                body()
+                if pp[0] == 0:
+                    head_body()
+            torch.cuda.synchronize(dev)
+            dist.barrier()
 
         if stage.sp is not None:   # a few eager steps first so that NCCL is fully initialised before the capture
             for _ in range(2):
@@ -309,6 +339,8 @@ class GraphedStage:
         with torch.cuda.stream(s):
             for _ in range(2):
                 y = body()
+                if self.head_in is not None:
+                    head_body()
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
@@ -316,6 +348,10 @@ class GraphedStage:
             self.y = body()
             if last_to_logits and stage.with_head:
                 self.logits = stage.head(self.y)
+        if self.head_in is not None:
+            self.head_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.head_graph):
+                self.logits = head_body()
         if dynamic:
             # the eager warm-up steps advanced the counters (and wrote slots >= L that later steps overwrite)
             stage.set_device_length(L, self.pos0)
@@ -325,6 +361,8 @@ class GraphedStage:
 
     def replay(self):
         self.graph.replay()
+        if self.head_graph is not None:
+            self.head_graph.replay()
         if self.dynamic:
             self.steps += 1
             sp = self.stage.sp

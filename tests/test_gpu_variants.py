@@ -16,7 +16,7 @@ sys.path.insert(0, %r)
 import test_gpu_parity as T
 for bits, L, sparse in ((4, 1100, True), (3, 611, True), (2, 530, True), (3, 200, False)):
     T.test_k_matvec_matches_oracle(bits, L, sparse)
-T.test_fused_attend_within_1e3_of_oracle_chain(4, 700, True, 3)
+T.test_fused_attend_within_1e3_of_oracle_chain(4, 700, True, 3, "fp32")   # the variants live in the exact (fp32-table) path
 print("VARIANT_OK")
 """ % HERE
 
