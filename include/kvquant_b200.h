@@ -197,10 +197,13 @@ KVQ_API int kvq_append_kv_fused(int bits, int H, int64_t Lmax, int64_t slot, int
  * Uncapped "orig" sparse path, 4-bit only (quant_cuda.cpp:347-399).
  * SpMV halves of ..._opt2_orig: balanced CSR (K; rows = tokens) quant_cuda_kernel.cu:523-614 and CSC (V; cols =
  * tokens) 616-689; the dense half is kvq_k_matvec / kvq_v_matvec with outliers == NULL.
+ * rows (K) / cols (V) are the CSR / CSC pointer arrays (num_rows + 1 entries); start_rows / start_cols / num_threads are
+ * the reference's work-split metadata: accepted for signature parity, not used (one warp per token here).  K takes the
+ * rope table of kvq_rope_table_build covering positions [0, pos_offset + num_rows).
  * ------------------------------------------------------------------------------------------------------------- */
 KVQ_API int kvq_k_spmv_csr(const int32_t* rows, const int32_t* cols, const int32_t* start_rows, const float* vals,
                    const float* q, float* mul, int H, int64_t L, int num_rows, int num_threads, int nnz,
-                   float theta, int pos_offset, void* stream);
+                   const float* rope_cos_sin, int64_t rope_npos, int pos_offset, void* stream);
 KVQ_API int kvq_v_spmv_csc(const int32_t* rows, const int32_t* cols, const int32_t* start_cols, const float* vals,
                    const float* score, float* mul, int H, int64_t L, int num_cols, int num_threads, int nnz,
                    void* stream);

@@ -47,7 +47,7 @@ SIGNATURES = {
     "kvq_p2p_close": (_c_int, [_p]),
     "kvq_p2p_free": (_c_int, [_p]),
     "kvq_attend_exchange_merge": (_c_int, [_p, _p, _c_int, _c_int, _c_int, _p, _p, _p, _p]),
-    "kvq_k_spmv_csr": (_c_int, [_p, _p, _p, _p, _p, _p, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_f, _c_int, _p]),
+    "kvq_k_spmv_csr": (_c_int, [_p, _p, _p, _p, _p, _p, _c_int, _c_i64, _c_int, _c_int, _c_int, _p, _c_i64, _c_int, _p]),
     "kvq_v_spmv_csc": (_c_int, [_p, _p, _p, _p, _p, _p, _c_int, _c_i64, _c_int, _c_int, _c_int, _p]),
     "kvq_append_k_orig": (_c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _c_int, _c_i64, _c_i64, _p]),
     "kvq_append_v_orig": (_c_int, [_p, _p, _p, _c_f, _c_f, _c_f, _p, _p, _p, _c_int, _c_i64, _c_i64, _p]),

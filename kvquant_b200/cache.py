@@ -164,22 +164,40 @@ class LayerCache:
         self.vaff[:, 0] = sf
         self.vaff[:, 1] = self.vlut[:, 0] - c0 * sf
 
+    def _vec(self, t, n, name, dtype=torch.float32):
+        """Device pointer of a caller tensor after the checks the C ABI cannot make: dtype, contiguity, this cache's
+        device, at least n elements (a short or foreign tensor would be read / written out of bounds)."""
+        qc._chk(t, dtype, name)
+        if t.device != self.device:
+            raise ValueError("%s is on %s, the cache lives on %s" % (name, t.device, self.device))
+        if t.numel() < n:
+            raise ValueError("%s has %d elements, %d needed" % (name, t.numel(), n))
+        return t.data_ptr()
+
     def _out_ptrs(self, which):
         """(values, indices) device pointers of a cache's outlier rows, or (None, None) when that cache is dense-only."""
         if which == "k":
             return (self.k_outliers.data_ptr(), self.k_outlier_idx.data_ptr()) if self.sparse_k else (None, None)
         return (self.v_outliers.data_ptr(), self.v_outlier_idx.data_ptr()) if self.sparse_v else (None, None)
 
+    _shared_scratch = {}     # device index -> one attend scratch shared by every cache that opted in (share_scratch)
+    share_scratch = False    # True: the caches of a device attend one after another on one stream (the decode harness);
+                             # at 1M tokens a private scratch per layer would cost 0.3 GB x layers
+
     def _ensure_scratch(self, need, slack):
         """Attend scratch, grown on demand.  A superseded buffer is kept alive (never handed back to the allocator):
         a captured CUDA graph bakes the raw pointer in, and growing must not happen inside a capture."""
-        if self._scratch is None or self._scratch.numel() < need:
+        cur = LayerCache._shared_scratch.get(self.device.index) if self.share_scratch else self._scratch
+        if cur is None or cur.numel() < need:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("attend scratch must be sized before graph capture (run one eager attend / "
                                    "attend_dyn with the same L_cap first)")
-            if self._scratch is not None:
-                self._retired.append(self._scratch)
-            self._scratch = torch.empty(int(need * slack) + 1024, dtype=torch.uint8, device=self.device)
+            if cur is not None:
+                self._retired.append(cur)
+            cur = torch.empty(int(need * slack) + 1024, dtype=torch.uint8, device=self.device)
+            if self.share_scratch:
+                LayerCache._shared_scratch[self.device.index] = cur
+        self._scratch = cur
 
     @_on_cache_device
     def append(self, k_new, v_new):
@@ -189,9 +207,9 @@ class LayerCache:
         s = torch.cuda.current_stream().cuda_stream
         _lib.check(self.lib.kvq_append_kv_fused(
             self.bits, self.H, self.Lmax, self.len, self.n_each,
-            qc._f32(k_new, "k_new"), self.kcache.data_ptr(), self.klut.data_ptr(), self.klut_sub.data_ptr(),
+            self._vec(k_new, self.hidden, "k_new"), self.kcache.data_ptr(), self.klut.data_ptr(), self.klut_sub.data_ptr(),
             self.thr_lower.data_ptr(), self.thr_upper.data_ptr(), *self._out_ptrs("k"),
-            qc._f32(v_new, "v_new"), self.vcache.data_ptr(), self.v_cent.data_ptr(),
+            self._vec(v_new, self.hidden, "v_new"), self.vcache.data_ptr(), self.v_cent.data_ptr(),
             self.v_cent_deq.data_ptr() if self.v_norm is not None else None, self.vlut.data_ptr(), self.vaff.data_ptr(),
             *self._out_ptrs("v"), s), "kvq_append_kv_fused")
         self.len += 1
@@ -202,6 +220,10 @@ class LayerCache:
         position.  Returns f32 [H,128].  lse (optional f32 [H]) receives the log-sum-exp of the scaled scores, which
         lets partial results over disjoint token ranges be merged exactly (sequence-sharded decode)."""
         L = self.len
+        if self.v_norm is not None and not self.use_native_v:
+            # the per-token LUT rows hold the un-normed centroids while the outlier residuals were taken against the
+            # Q-Norm table: the legacy-LUT V kernel would mix the two
+            raise NotImplementedError("V Q-Norm needs the native V form (use_native_v=True)")
         self._ensure_scratch(self.lib.kvq_attend_scratch_bytes(self.H, max(L, 1)), 1.25)
         pos_offset = self.n_sink + self.pos_base
         rope, rope_h, npos = qc.rope_tables(self.device, rope_theta, L + pos_offset + 1)
@@ -209,13 +231,13 @@ class LayerCache:
         out = self._out if out is None else out
         ns = self.n_sink if self.sink_k is not None else 0
         _lib.check(self.lib.kvq_attend(
-            self.bits, qc._f32(q, "q"), self.kcache.data_ptr(), self.klut_deq.data_ptr(), *self._out_ptrs("k"),
+            self.bits, self._vec(q, self.hidden, "q"), self.kcache.data_ptr(), self.klut_deq.data_ptr(), *self._out_ptrs("k"),
             self.vcache.data_ptr(), self.vlut.data_ptr(),
             self.v_cent_deq.data_ptr() if self.use_native_v else None, self.vaff.data_ptr() if self.use_native_v else None,
             *self._out_ptrs("v"),
             self.n_out, self.H, self.Lmax, L, rope.data_ptr(), npos, float(rope_theta), pos_offset,
             self.sink_k.data_ptr() if ns else None, self.sink_v.data_ptr() if ns else None, ns,
-            out.data_ptr(), lse.data_ptr() if lse is not None else None, self._scratch.data_ptr(),
+            self._vec(out, self.hidden, "out"), self._vec(lse, self.H, "lse") if lse is not None else None, self._scratch.data_ptr(),
             rope_h.data_ptr() if fast else None, torch.cuda.current_stream().cuda_stream), "kvq_attend")
         return out
 
@@ -226,10 +248,10 @@ class LayerCache:
         advanced: the caller owns the device counter (kvq_dec_counter_add) and re-syncs `len` when it leaves the graph."""
         s = torch.cuda.current_stream().cuda_stream
         _lib.check(self.lib.kvq_append_kv_fused_dyn(
-            self.bits, self.H, self.Lmax, len_dev.data_ptr(), int(slot_add), self.n_each,
-            qc._f32(k_new, "k_new"), self.kcache.data_ptr(), self.klut.data_ptr(), self.klut_sub.data_ptr(),
+            self.bits, self.H, self.Lmax, self._vec(len_dev, 1, "len_dev", torch.int64), int(slot_add), self.n_each,
+            self._vec(k_new, self.hidden, "k_new"), self.kcache.data_ptr(), self.klut.data_ptr(), self.klut_sub.data_ptr(),
             self.thr_lower.data_ptr(), self.thr_upper.data_ptr(), *self._out_ptrs("k"),
-            qc._f32(v_new, "v_new"), self.vcache.data_ptr(), self.v_cent.data_ptr(),
+            self._vec(v_new, self.hidden, "v_new"), self.vcache.data_ptr(), self.v_cent.data_ptr(),
             self.v_cent_deq.data_ptr() if self.v_norm is not None else None, self.vlut.data_ptr(), self.vaff.data_ptr(),
             *self._out_ptrs("v"), s), "kvq_append_kv_fused_dyn")
 
@@ -247,12 +269,12 @@ class LayerCache:
         out = self._out if out is None else out
         ns = self.n_sink if self.sink_k is not None else 0
         _lib.check(self.lib.kvq_attend_dyn(
-            self.bits, qc._f32(q, "q"), self.kcache.data_ptr(), self.klut_deq.data_ptr(), *self._out_ptrs("k"),
+            self.bits, self._vec(q, self.hidden, "q"), self.kcache.data_ptr(), self.klut_deq.data_ptr(), *self._out_ptrs("k"),
             self.vcache.data_ptr(), self.v_cent_deq.data_ptr(), self.vaff.data_ptr(), *self._out_ptrs("v"),
-            self.n_out, self.H, self.Lmax, L_cap, len_dev.data_ptr(), int(len_add), rope.data_ptr(), npos,
+            self.n_out, self.H, self.Lmax, L_cap, self._vec(len_dev, 1, "len_dev", torch.int64), int(len_add), rope.data_ptr(), npos,
             float(rope_theta), pos_offset, self.sink_k.data_ptr() if ns else None,
-            self.sink_v.data_ptr() if ns else None, ns, out.data_ptr(),
-            lse.data_ptr() if lse is not None else None, self._scratch.data_ptr(),
+            self.sink_v.data_ptr() if ns else None, ns, self._vec(out, self.hidden, "out"),
+            self._vec(lse, self.H, "lse") if lse is not None else None, self._scratch.data_ptr(),
             rope_h.data_ptr() if fast else None, torch.cuda.current_stream().cuda_stream), "kvq_attend_dyn")
         return out
 
@@ -455,7 +477,7 @@ class QuantV(torch.nn.Module):
             maxval, minval = v.max(), v.min()
             offset = (maxval + minval) / 2
             sf = (maxval - minval) / 2
-        lut_t = self.lut.float() * sf.float() + offset.float()   # device math, no .item() sync
+        lut_t = self.lut.float() * sf.float() + offset.float()   # device math (the reference calls .item() three times here)
         self.lookup_table[slot] = lut_t
         score = score.transpose(0, 1).contiguous()
         if self.include_sparse:

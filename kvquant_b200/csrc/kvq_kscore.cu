@@ -814,6 +814,7 @@ int kvq_k_matvec(int bits, const float* q, const int32_t* cache, float* mul, con
   if (B <= 0 || H <= 0 || L < 0 || L > Lmax || pos_offset < 0 || Lmax >= ((int64_t)1 << 30)) return KVQ_E_SHAPE;
   if ((outliers == nullptr) != (outlier_idx == nullptr)) return KVQ_E_NULL;
   if (outliers && (B != 1 || n_out <= 0)) return KVQ_E_SHAPE;  // reference: sparse part is batch-1 only (DK.cu:3605)
+  if (outliers && H > 64) return KVQ_E_SHAPE;                  // the outlier scatter keys its segments on token * 64 + head
   if (rope_npos < L + pos_offset) return KVQ_E_SHAPE;
   if (L == 0) return 0;
   for (int b = 0; b < B; ++b) {

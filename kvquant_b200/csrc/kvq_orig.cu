@@ -82,79 +82,78 @@ __global__ void __launch_bounds__(kOrigThreads, 1) orig_append_kernel(
   }
 }
 
-// SPMV_ATOMIC_CSR_ROPE_BALANCED semantics (quant_cuda_kernel.cu:523-614)
-__global__ void csr_k_spmv_kernel(const int* __restrict__ rows, const int* __restrict__ cols,
-                                  const int* __restrict__ startrows, const float* __restrict__ mat,
-                                  const float* __restrict__ vec, float* __restrict__ mul, int num_rows,
-                                  int64_t seqlen, int num_threads, int nnz, float rope_theta, int pos_offset) {
-  const int headdim = kHeadDim;
-  const int per = (nnz + num_threads - 1) / num_threads;
-  const int th = blockIdx.x * blockDim.x + threadIdx.x;
-  if (th >= num_threads) return;
-  int row = startrows[th];
-  int nextrow = -1;
-  if (row != -1) {
-    nextrow = rows[row + 1];
-    while (nextrow == th * per) {  // do not start on an empty row
-      row += 1;
-      if (row < num_rows) nextrow = rows[row + 1];
-      else break;
-    }
-  }
-  if (th * per >= nnz || row == -1) return;
-  const int end = min(nnz, (th + 1) * per);
-  for (int i = th * per; i < end; ++i) {
-    const int col = cols[i];
-    const float v = mat[i];
-    const int head = col / headdim, ch = col % headdim;
-    const float theta = powf(rope_theta, (-2 * __int2float_rd(ch % (headdim / 2)) / headdim));
-    const float sign = (ch < headdim / 2) ? 1.f : -1.f;
-    const float c = cosf(theta * (row + pos_offset));
-    const float s = sinf(theta * (row + pos_offset));
-    const int col2 = ((ch + headdim / 2) % headdim) + head * headdim;
-    float dot = v * c * vec[col];
-    dot += sign * v * s * vec[col2];
-    atomicAdd(&mul[(int64_t)head * seqlen + row], dot);
-    while (i + 1 == nextrow) {  // row finished (skip empty rows)
-      row += 1;
-      if (row < num_rows) nextrow = rows[row + 1];
-      else { nextrow = -1; break; }
+// ---- SpMV halves of the uncapped path ----------------------------------------------------------------------------------
+// Same results as SPMV_ATOMIC_CSR_ROPE_BALANCED / SPMV_ATOMIC_CSC_BALANCED (quant_cuda_kernel.cu:523-614, 616-689), built
+// the way the capped kernels of this library are (kvq_kscore.cu): the reference gives every thread ten consecutive
+// non-zeros, walks the row pointers to find out which token each belongs to, re-evaluates powf / cosf / sinf per
+// non-zero and issues one global atomic per non-zero (its start_rows / num_threads arguments only describe that work
+// split and do not influence the result -- they are accepted and ignored here).
+//
+// K (CSR, row = token): one WARP per token.  The lanes stride over the token's non-zeros (coalesced), cos/sin come from
+// the rope table (the reference's own expressions, evaluated once per (pair, position)), and because a row is sorted by
+// channel the non-zeros of one head are adjacent: a warp-level segmented sum leaves one atomic per (token, head).
+constexpr int kSpmvThreads = 256;
+
+__global__ void __launch_bounds__(kSpmvThreads) csr_k_spmv_kernel(
+    const int* __restrict__ row_ptr, const int* __restrict__ cols, const float* __restrict__ vals,
+    const float* __restrict__ q, float* __restrict__ mul, int num_rows, int64_t seqlen,
+    const float2* __restrict__ rope, int64_t rope_npos, int pos_offset) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * kSpmvThreads) >> 5;
+  for (int row = (blockIdx.x * kSpmvThreads + threadIdx.x) >> 5; row < num_rows; row += warps) {
+    const int beg = row_ptr[row], end = row_ptr[row + 1];
+    for (int base = beg; base < end; base += 32) {      // warp-uniform trip count
+      const int i = base + lane;
+      float contrib = 0.f;
+      int head = -1 - lane;                              // idle lanes never merge
+      if (i < end) {
+        const int col = cols[i];
+        const float v = vals[i];
+        head = col >> 7;
+        const int ch = col & (kHeadDim - 1);
+        const float2 cs = rope[(int64_t)(ch & (kHalf - 1)) * rope_npos + row + pos_offset];
+        float dot = v * cs.x * __ldg(q + col);                                  // operation order of DK.cu:599-601
+        dot += ((ch < kHalf) ? 1.f : -1.f) * v * cs.y * __ldg(q + (col ^ kHalf));
+        contrib = dot;
+      }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {                 // segmented sum over runs of equal heads
+        const float v2 = __shfl_down_sync(0xffffffffu, contrib, o);
+        const int h2 = __shfl_down_sync(0xffffffffu, head, o);
+        if (lane + o < 32 && h2 == head) contrib += v2;
+      }
+      const int hprev = __shfl_up_sync(0xffffffffu, head, 1);
+      if (i < end && (lane == 0 || hprev != head)) atomicAdd(&mul[(int64_t)head * seqlen + row], contrib);
     }
   }
 }
 
-// SPMV_ATOMIC_CSC_BALANCED semantics (quant_cuda_kernel.cu:616-689)
-__global__ void csc_v_spmv_kernel(const int* __restrict__ rows, const int* __restrict__ cols,
-                                  const int* __restrict__ startcols, const float* __restrict__ mat,
-                                  const float* __restrict__ vec, float* __restrict__ mul, int num_cols,
-                                  int64_t seqlen, int num_threads, int nnz) {
-  const int headdim = kHeadDim;
-  const int per = (nnz + num_threads - 1) / num_threads;
-  const int th = blockIdx.x * blockDim.x + threadIdx.x;
-  if (th >= num_threads) return;
-  int col = startcols[th];
-  int nextcol = -1;
-  if (col != -1) {
-    nextcol = cols[col + 1];
-    while (nextcol == th * per) {
-      col += 1;
-      if (col < num_cols) nextcol = cols[col + 1];
-      else break;
+// V (CSC, column = token): one warp per token again; the products value * score[head, token] are summed per CHANNEL in a
+// shared-memory image of the output that the CTA flushes once at the end -- `hidden` global atomics per CTA instead
+// of one per non-zero onto the same 4096 addresses.
+__global__ void __launch_bounds__(kSpmvThreads) csc_v_spmv_kernel(
+    const int* __restrict__ rows, const int* __restrict__ col_ptr, const float* __restrict__ vals,
+    const float* __restrict__ score, float* __restrict__ mul, int num_cols, int64_t seqlen, int hidden) {
+  extern __shared__ float s_acc[];                       // [hidden]
+  for (int j = threadIdx.x; j < hidden; j += kSpmvThreads) s_acc[j] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * kSpmvThreads) >> 5;
+  for (int col = (blockIdx.x * kSpmvThreads + threadIdx.x) >> 5; col < num_cols; col += warps) {
+    const int beg = col_ptr[col], end = col_ptr[col + 1];
+    for (int i = beg + lane; i < end; i += 32) {
+      const int ch = rows[i];
+      atomicAdd(&s_acc[ch], vals[i] * __ldg(score + (int64_t)(ch >> 7) * seqlen + col));
     }
   }
-  if (th * per >= nnz || col == -1) return;
-  const int end = min(nnz, (th + 1) * per);
-  for (int i = th * per; i < end; ++i) {
-    const int row = rows[i];
-    const int head = row / headdim;
-    atomicAdd(&mul[row], mat[i] * vec[(int64_t)head * seqlen + col]);
-    while (i + 1 == nextcol) {
-      col += 1;
-      if (col < num_cols) nextcol = cols[col + 1];
-      else { nextcol = -1; break; }
-    }
+  __syncthreads();
+  for (int j = threadIdx.x; j < hidden; j += kSpmvThreads) {
+    const float v = s_acc[j];
+    if (v != 0.f) atomicAdd(&mul[j], v);
   }
 }
+
+int num_sms_cached();
 
 }  // namespace kvq
 
@@ -163,13 +162,17 @@ using namespace kvq;
 extern "C" {
 
 int kvq_k_spmv_csr(const int32_t* rows, const int32_t* cols, const int32_t* start_rows, const float* vals,
-                   const float* q, float* mul, int H, int64_t L, int num_rows, int num_threads, int nnz, float theta,
-                   int pos_offset, void* stream) {
-  if (!rows || !cols || !start_rows || !vals || !q || !mul) return KVQ_E_NULL;
-  if (H <= 0 || L < 0 || num_threads < 0 || nnz < 0) return KVQ_E_SHAPE;
-  if (num_threads == 0 || nnz == 0) return 0;
-  csr_k_spmv_kernel<<<(num_threads + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      rows, cols, start_rows, vals, q, mul, num_rows, L, num_threads, nnz, theta, pos_offset);
+                   const float* q, float* mul, int H, int64_t L, int num_rows, int num_threads, int nnz,
+                   const float* rope_cos_sin, int64_t rope_npos, int pos_offset, void* stream) {
+  (void)start_rows; (void)num_threads;                  // the reference's work split, not part of the result
+  if (!rows || !cols || !vals || !q || !mul || !rope_cos_sin) return KVQ_E_NULL;
+  if (H <= 0 || L < 0 || nnz < 0 || num_rows < 0 || num_rows > L || rope_npos < num_rows + pos_offset) return KVQ_E_SHAPE;
+  if (nnz == 0 || num_rows == 0) return 0;
+  int grid = (num_rows * 32 + kSpmvThreads - 1) / kSpmvThreads;
+  const int cap = num_sms_cached() * 8;
+  if (grid > cap) grid = cap;
+  csr_k_spmv_kernel<<<grid, kSpmvThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      rows, cols, vals, q, mul, num_rows, L, reinterpret_cast<const float2*>(rope_cos_sin), rope_npos, pos_offset);
   KVQ_LAUNCH_CHECK();
   return 0;
 }
@@ -177,11 +180,16 @@ int kvq_k_spmv_csr(const int32_t* rows, const int32_t* cols, const int32_t* star
 int kvq_v_spmv_csc(const int32_t* rows, const int32_t* cols, const int32_t* start_cols, const float* vals,
                    const float* score, float* mul, int H, int64_t L, int num_cols, int num_threads, int nnz,
                    void* stream) {
-  if (!rows || !cols || !start_cols || !vals || !score || !mul) return KVQ_E_NULL;
-  if (H <= 0 || L < 0 || num_threads < 0 || nnz < 0) return KVQ_E_SHAPE;
-  if (num_threads == 0 || nnz == 0) return 0;
-  csc_v_spmv_kernel<<<(num_threads + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      rows, cols, start_cols, vals, score, mul, num_cols, L, num_threads, nnz);
+  (void)start_cols; (void)num_threads;
+  if (!rows || !cols || !vals || !score || !mul) return KVQ_E_NULL;
+  if (H <= 0 || H * kHeadDim > 12288 || L < 0 || nnz < 0 || num_cols < 0 || num_cols > L) return KVQ_E_SHAPE;
+  if (nnz == 0 || num_cols == 0) return 0;
+  const int hidden = H * kHeadDim;
+  int grid = (num_cols * 32 + kSpmvThreads - 1) / kSpmvThreads;
+  const int cap = num_sms_cached() * 2;
+  if (grid > cap) grid = cap;
+  csc_v_spmv_kernel<<<grid, kSpmvThreads, hidden * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      rows, cols, vals, score, mul, num_cols, L, hidden);
   KVQ_LAUNCH_CHECK();
   return 0;
 }

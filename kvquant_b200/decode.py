@@ -83,6 +83,7 @@ class DecoderLayer:
                                           device=device, include_sparse=cfg.include_sparse,
                                           sparsity_threshold=cfg.sparsity_threshold, n_sink=cfg.n_sink,
                                           sparse_v=cfg.sparse_v)
+        self.cache.share_scratch = True     # the layers of a stage attend one after another on one stream
         if cfg.n_sink and with_sinks:
             sk = (torch.randn((cfg.n_heads, HEAD_DIM, cfg.n_sink), generator=gen, device=device)).half()
             sv = (torch.randn((cfg.n_heads, cfg.n_sink, HEAD_DIM), generator=gen, device=device)).half()
@@ -356,8 +357,8 @@ class GraphedStage:
             # the eager warm-up steps advanced the counters (and wrote slots >= L that later steps overwrite)
             stage.set_device_length(L, self.pos0)
             stage.set_len(L)
-        else:
-            stage.set_len(L + 1)
+        elif stage.sp is None or stage.sp[0] == stage.sp[1] - 1:
+            stage.set_len(L + 1)          # (sp: only the last shard appended a token)
 
     def replay(self):
         self.graph.replay()

@@ -286,9 +286,10 @@ def vecquant4matmul_nuq_perchannel_transposed_rope_mha_batched_fused_opt2_orig(
     lib = _lib.load()
     H, _ = _cache_dims(mat, 4)
     with torch.cuda.device(mat.device):
+        rope, npos = rope_table(mat.device, rope_theta, int(kcachelen) + int(pos_offset))
         _lib.check(lib.kvq_k_spmv_csr(_i32(rows, "rows"), _i32(cols, "cols"), _i32(startrows, "startrows"),
                                       _f32(spmat, "spmat"), _f32(vec, "vec"), _f32(mul, "mul"), H, int(kcachelen),
-                                      int(num_rows), int(num_threads), int(nnz), float(rope_theta), int(pos_offset),
+                                      int(num_rows), int(num_threads), int(nnz), rope.data_ptr(), npos, int(pos_offset),
                                       _stream()), "spmv csr")
 
 
