@@ -215,6 +215,7 @@ __device__ void radix_select_both(const uint32_t* keys, int n, int k, SelectSmem
       }
       uint32_t above = incl - tot;  // elements in higher lanes' bins
       const uint32_t kr = sel.krem[s];
+      __syncwarp();   // every lane has read krem before the one winning lane below rewrites it (racecheck: WAR hazard)
       // the k-th element lies in this lane's 8 bins iff above < kr <= above + tot
       if (above < kr && kr <= above + tot) {
 #pragma unroll

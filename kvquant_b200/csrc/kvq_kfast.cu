@@ -35,6 +35,7 @@ struct KFParams {
   float* out;                // [H][out_stride]
   float* gmax;               // [H] or null
   int64_t Lmax, L, out_stride, rope_npos, range;
+  int64_t t0;                // first token of this launch (long caches are walked in L2-sized blocks)
   const int64_t* len_dev;
   int64_t len_add;
   int H, G, pos_offset, accumulate, n_stages;
@@ -225,13 +226,13 @@ __global__ void __launch_bounds__(kKFThreads, 1) k_fast_kernel(const __grid_cons
   int64_t L_eff = p.L;
   int64_t range = p.range;
   if (p.len_dev != nullptr) {
-    const int64_t l = *p.len_dev + p.len_add;
+    const int64_t l = *p.len_dev + p.len_add - p.t0;
     L_eff = l < 0 ? 0 : (l < p.L ? l : p.L);
     const int64_t r = (L_eff + gridDim.x - 1) / gridDim.x;
     range = (r + 31) & ~(int64_t)31;
   }
-  const int64_t t_begin = (int64_t)blockIdx.x * range;
-  const int64_t t_limit = min(L_eff, t_begin + range);
+  const int64_t t_begin = p.t0 + (int64_t)blockIdx.x * range;
+  const int64_t t_limit = p.t0 + min(L_eff, ((int64_t)blockIdx.x + 1) * range);
   if (t_begin >= t_limit) return;
   const int ncols = (int)((t_limit - t_begin + kKFColTok - 1) / kKFColTok);      // 16-token warp columns
   const int nrounds = (ncols + kKFWarps - 1) / kKFWarps;
@@ -367,10 +368,13 @@ __global__ void rope_table_half_kernel(uint32_t* __restrict__ out, float rope_th
 int num_sms_cached();
 
 template <int BITS>
-static int launch_k_fast(KFParams p, const float* q, const float* lut, uint32_t* qtab, const int32_t* cache, cudaStream_t st) {
+static int launch_k_fast(KFParams p, const float* q, const float* lut, uint32_t* qtab, const int32_t* cache, int run_prep,
+                         cudaStream_t st) {
   using C = KFCfg<BITS>;
-  k_fast_prep_kernel<BITS><<<p.H, kHeadDim, 0, st>>>(q, lut, qtab);
-  KVQ_LAUNCH_CHECK();
+  if (run_prep) {
+    k_fast_prep_kernel<BITS><<<p.H, kHeadDim, 0, st>>>(q, lut, qtab);
+    KVQ_LAUNCH_CHECK();
+  }
   const int groups = (p.H + C::GMAX - 1) / C::GMAX;
   p.G = (p.H + groups - 1) / groups;
   const uint32_t tab_span = (uint32_t)p.G * C::kHeadTab;
@@ -403,18 +407,19 @@ static int launch_k_fast(KFParams p, const float* q, const float* lut, uint32_t*
 // when accumulate != 0.
 int k_fast_dispatch(int bits, const float* q, const int32_t* cache, float* scores, int64_t score_stride, const float* lut,
                     int H, int64_t Lmax, int64_t L, const void* rope_half, int64_t rope_npos, int pos_offset, float* gmax,
-                    float scale, int accumulate, const int64_t* len_dev, int64_t len_add, void* qtab, cudaStream_t st) {
+                    float scale, int accumulate, const int64_t* len_dev, int64_t len_add, void* qtab, int64_t t0,
+                     int run_prep, cudaStream_t st) {
   KFParams p{};
   p.qtab = static_cast<const uint32_t*>(qtab);
   p.rope_h = static_cast<const uint32_t*>(rope_half);
   p.out = scores; p.gmax = gmax;
   p.Lmax = Lmax; p.L = L; p.out_stride = score_stride; p.rope_npos = rope_npos;
-  p.len_dev = len_dev; p.len_add = len_add;
+  p.len_dev = len_dev; p.len_add = len_add; p.t0 = t0;
   p.H = H; p.pos_offset = pos_offset; p.accumulate = accumulate; p.scale = scale;
   switch (bits) {
-    case 4: return launch_k_fast<4>(p, q, lut, static_cast<uint32_t*>(qtab), cache, st);
-    case 3: return launch_k_fast<3>(p, q, lut, static_cast<uint32_t*>(qtab), cache, st);
-    case 2: return launch_k_fast<2>(p, q, lut, static_cast<uint32_t*>(qtab), cache, st);
+    case 4: return launch_k_fast<4>(p, q, lut, static_cast<uint32_t*>(qtab), cache, run_prep, st);
+    case 3: return launch_k_fast<3>(p, q, lut, static_cast<uint32_t*>(qtab), cache, run_prep, st);
+    case 2: return launch_k_fast<2>(p, q, lut, static_cast<uint32_t*>(qtab), cache, run_prep, st);
     default: return KVQ_E_BITS;
   }
 }

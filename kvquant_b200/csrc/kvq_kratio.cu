@@ -43,6 +43,7 @@ struct KRParams {
   float* out;                // [H][out_stride]
   float* gmax;               // [H] or null
   int64_t Lmax, L, out_stride, rope_npos, range;
+  int64_t t0;                // first token of this launch (long caches are walked in L2-sized blocks)
   const int64_t* len_dev;
   int64_t len_add;
   int H, G, pos_offset, accumulate, n_stages;
@@ -188,13 +189,13 @@ __global__ void __launch_bounds__(kKRThreads, 1) k_ratio_kernel(const __grid_con
   int64_t L_eff = p.L;
   int64_t range = p.range;
   if (p.len_dev != nullptr) {
-    const int64_t l = *p.len_dev + p.len_add;
+    const int64_t l = *p.len_dev + p.len_add - p.t0;
     L_eff = l < 0 ? 0 : (l < p.L ? l : p.L);
     const int64_t r = (L_eff + gridDim.x - 1) / gridDim.x;
     range = (r + 31) & ~(int64_t)31;
   }
-  const int64_t t_begin = (int64_t)blockIdx.x * range;
-  const int64_t t_limit = min(L_eff, t_begin + range);
+  const int64_t t_begin = p.t0 + (int64_t)blockIdx.x * range;
+  const int64_t t_limit = p.t0 + min(L_eff, ((int64_t)blockIdx.x + 1) * range);
   if (t_begin >= t_limit) return;
   const int ncols = (int)((t_limit - t_begin + kKRColTok - 1) / kKRColTok);
   const int nrounds = (ncols + kKRWarps - 1) / kKRWarps;
@@ -319,10 +320,12 @@ int num_sms_cached();
 
 template <int BITS>
 static int launch_k_ratio(KRParams p, const float* q, const float* lut, float* qtab, float* qrat, const int32_t* cache,
-                          cudaStream_t st) {
+                          int run_prep, cudaStream_t st) {
   using C = KRCfg<BITS>;
-  k_ratio_prep_kernel<BITS><<<p.H, kHeadDim, 0, st>>>(q, lut, qtab, qrat);
-  KVQ_LAUNCH_CHECK();
+  if (run_prep) {
+    k_ratio_prep_kernel<BITS><<<p.H, kHeadDim, 0, st>>>(q, lut, qtab, qrat);
+    KVQ_LAUNCH_CHECK();
+  }
   const int groups = (p.H + C::GMAX - 1) / C::GMAX;
   p.G = (p.H + groups - 1) / groups;
   const uint32_t tab_span = (uint32_t)p.G * (C::kHeadTab + C::kHeadRat);
@@ -355,7 +358,8 @@ static int launch_k_ratio(KRParams p, const float* q, const float* lut, float* q
 // when accumulate != 0.  qtab: scratch of H * 128 * (2^bits + 1) floats.
 int k_ratio_dispatch(int bits, const float* q, const int32_t* cache, float* scores, int64_t score_stride, const float* lut,
                      int H, int64_t Lmax, int64_t L, const float* rope, int64_t rope_npos, int pos_offset, float* gmax,
-                     float scale, int accumulate, const int64_t* len_dev, int64_t len_add, void* qtab, cudaStream_t st) {
+                     float scale, int accumulate, const int64_t* len_dev, int64_t len_add, void* qtab, int64_t t0,
+                     int run_prep, cudaStream_t st) {
   KRParams p{};
   float* tab = static_cast<float*>(qtab);
   float* rat = tab + (size_t)H * kHeadDim * (1 << bits);
@@ -363,12 +367,12 @@ int k_ratio_dispatch(int bits, const float* q, const int32_t* cache, float* scor
   p.rope = reinterpret_cast<const float2*>(rope);
   p.out = scores; p.gmax = gmax;
   p.Lmax = Lmax; p.L = L; p.out_stride = score_stride; p.rope_npos = rope_npos;
-  p.len_dev = len_dev; p.len_add = len_add;
+  p.len_dev = len_dev; p.len_add = len_add; p.t0 = t0;
   p.H = H; p.pos_offset = pos_offset; p.accumulate = accumulate; p.scale = scale;
   switch (bits) {
-    case 4: return launch_k_ratio<4>(p, q, lut, tab, rat, cache, st);
-    case 3: return launch_k_ratio<3>(p, q, lut, tab, rat, cache, st);
-    case 2: return launch_k_ratio<2>(p, q, lut, tab, rat, cache, st);
+    case 4: return launch_k_ratio<4>(p, q, lut, tab, rat, cache, run_prep, st);
+    case 3: return launch_k_ratio<3>(p, q, lut, tab, rat, cache, run_prep, st);
+    case 2: return launch_k_ratio<2>(p, q, lut, tab, rat, cache, run_prep, st);
     default: return KVQ_E_BITS;
   }
 }

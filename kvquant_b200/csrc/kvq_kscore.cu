@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(kOutPersThreads) k_outlier_pers_kernel(
     const float* __restrict__ q, const float* __restrict__ outliers, const int32_t* __restrict__ outlier_idx,
     float* __restrict__ out, int64_t stride_h, int64_t stride_t, int64_t L, int H, int n_out,
     const float2* __restrict__ rope, int64_t rope_npos, int pos_offset, float scale,
-    const int64_t* __restrict__ len_dev, int64_t len_add, const uint32_t* __restrict__ rope_h) {
+    const int64_t* __restrict__ len_dev, int64_t len_add, const uint32_t* __restrict__ rope_h, float rope_theta) {
   extern __shared__ float2 s_qq[];                       // [H*128] = (q[c], q[c^64])
   if (len_dev != nullptr) {                              // device-resident length: L is the cap the grid was sized for
     const int64_t l = *len_dev + len_add;
@@ -590,7 +590,15 @@ __global__ void __launch_bounds__(kOutPersThreads) k_outlier_pers_kernel(
       key = (int)(t * 64u) + h;                          // t < 2^25
       if (v != 0.f) {   // pads / non-outliers contribute exactly 0 in the reference too
         float2 cs;
-        if (rope_h != nullptr) {   // fp16 mode: the half2 table the dense kernel streams (half the bytes per gather)
+        if (rope_theta > 0.f) {
+          // long contexts: the rope table no longer fits L2 and a scattered 8-byte gather costs a 32-byte DRAM sector
+          // (1M tokens: 17x the 128K cost for 8x the tokens) -- evaluate the table builder's own expressions instead
+          // (same device functions, same arguments: bit-identical values)
+          const int headdim = kHeadDim, headdim2 = headdim / 2;
+          const float th = powf(rope_theta, (-2 * __int2float_rd((c & (kHalf - 1)) % headdim2) / __int2float_rd(headdim)));
+          const int pos = (int)t + pos_offset;
+          cs = make_float2(cosf(th * pos), sinf(th * pos));
+        } else if (rope_h != nullptr) {   // fp16 mode: the half2 table the dense kernel streams (half the bytes per gather)
           uint32_t u;
           asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(u)
                        : "l"(rope_h + (int64_t)(c & (kHalf - 1)) * rope_npos + t + pos_offset), "l"(pol_keep));
@@ -621,6 +629,14 @@ static int k_out_impl_table() {   // KVQ_KOUT_IMPL=table selects the non-persist
   static int v = -1;
   if (v < 0) { const char* e = getenv("KVQ_KOUT_IMPL"); v = (e && e[0] == 't') ? 1 : 0; }
   return v;
+}
+
+// rope tables beyond this many positions are not gathered from by the outlier scatter (KVQ_KOUT_DIRECT_NPOS overrides):
+// 64 pairs x 8 bytes x 160K positions = 80 MB, about what stays resident in the 126 MB L2 next to the streams
+static bool k_out_direct(int64_t n_positions) {
+  static int64_t thr = -1;
+  if (thr < 0) { const char* e = getenv("KVQ_KOUT_DIRECT_NPOS"); thr = e ? atoll(e) : 160 * 1024; }
+  return n_positions > thr;
 }
 
 // zero_first = 1: `out` is a fresh score buffer (fused path) and is cleared before the scatter
@@ -663,7 +679,8 @@ static int launch_k_outliers(const KParams& p, int zero_first, float scale, cuda
   const int64_t sh = p.opart != nullptr ? 1 : p.out_stride, stt = p.opart != nullptr ? p.opart_stride : 1;
   k_outlier_pers_kernel<<<grid, kOutPersThreads, smem, st>>>(p.q, p.outliers, p.outlier_idx, dst, sh, stt, p.L,
                                                              p.H, p.n_out, p.rope, p.rope_npos, p.pos_offset, scale,
-                                                             p.len_dev, p.len_add, p.rope_h);
+                                                             p.len_dev, p.len_add, p.rope_h,
+                                                             k_out_direct(p.L + p.pos_offset) ? p.theta : 0.f);
   KVQ_LAUNCH_CHECK();
   return 0;
 }
@@ -770,26 +787,47 @@ int k_scores_fused(int bits, const float* q, const int32_t* cache, float* scores
 // (kvq_kratio.cu); otherwise the fp16-table form (kvq_kfast.cu).
 int k_scores_fused_fast(int bits, const float* q, const int32_t* cache, float* scores, int64_t score_stride,
                         const float* lut, const float* outliers, const int32_t* outlier_idx, int n_out, int H,
-                        int64_t Lmax, int64_t L, const float* rope, const void* rope_half, int64_t rope_npos,
+                        int64_t Lmax, int64_t L, const float* rope, const void* rope_half, int64_t rope_npos, float theta,
                         int pos_offset, float* gmax, float scale, const int64_t* len_dev, int64_t len_add, void* qtab,
                         cudaStream_t st) {
-  int accumulate = 0;
-  if (outliers != nullptr) {
-    KParams p{};
-    p.len_dev = len_dev; p.len_add = len_add;
-    p.q = q; p.out = scores; p.outliers = outliers; p.outlier_idx = outlier_idx;
-    p.rope = reinterpret_cast<const float2*>(rope); p.rope_h = static_cast<const uint32_t*>(rope_half);
-    p.Lmax = Lmax; p.L = L; p.out_stride = score_stride; p.rope_npos = rope_npos;
-    p.H = H; p.n_out = n_out; p.pos_offset = pos_offset;
-    const int rc = launch_k_outliers(p, /*zero_first=*/1, 1.f, st);
-    if (rc != 0) return rc;
-    accumulate = 1;
+  // KVQ_K_BLOCK=<tokens>: walk the cache in blocks whose score rows (H x block floats) stay L2-resident between the
+  // outlier scatter (atomic adds) and the dense kernel.  Measured at 1M tokens, 3-bit, 1 % outliers with 128K blocks:
+  // outlier scatter 8 x 0.090 ms (one pass: 0.79 ms by table gather, 0.68 ms with direct cos/sin), dense kernel
+  // 8 x 0.156 ms (one pass: 1.17 ms), attend 3.13 ms vs 2.96 ms -- no gain, so the default is ONE pass; the switch
+  // stays for A/B runs and is covered by tests/test_gpu_variants.py.
+  static int64_t kBlock = 0;
+  if (kBlock == 0) {
+    const char* e = getenv("KVQ_K_BLOCK");
+    kBlock = e ? (atoll(e) + 31) / 32 * 32 : ((int64_t)1 << 40);
+    if (kBlock < 32) kBlock = (int64_t)1 << 40;
   }
-  if (rope_half == nullptr)   // exact mode: fp32 ratio form (kvq_kratio.cu)
-    return k_ratio_dispatch(bits, q, cache, scores, score_stride, lut, H, Lmax, L, rope, rope_npos, pos_offset, gmax, scale,
-                            accumulate, len_dev, len_add, qtab, st);
-  return k_fast_dispatch(bits, q, cache, scores, score_stride, lut, H, Lmax, L, rope_half, rope_npos, pos_offset, gmax,
-                         scale, accumulate, len_dev, len_add, qtab, st);
+  int run_prep = 1;
+  for (int64_t t0 = 0; t0 < L; t0 += kBlock) {
+    const int64_t Lb = (L - t0 > kBlock + kBlock / 2) ? kBlock : (L - t0);   // the last block may be up to 1.5 blocks
+    int accumulate = 0;
+    if (outliers != nullptr) {
+      KParams p{};
+      p.len_dev = len_dev; p.len_add = len_add - t0;
+      p.q = q; p.out = scores + t0; p.outliers = outliers + t0 * n_out; p.outlier_idx = outlier_idx + t0 * n_out;
+      p.rope = reinterpret_cast<const float2*>(rope); p.rope_h = static_cast<const uint32_t*>(rope_half);
+      p.Lmax = Lmax; p.L = Lb; p.out_stride = score_stride; p.rope_npos = rope_npos;
+      p.H = H; p.n_out = n_out; p.pos_offset = pos_offset + (int)t0; p.theta = theta;
+      cudaError_t e = cudaMemset2DAsync(scores + t0, sizeof(float) * (size_t)score_stride, 0, sizeof(float) * (size_t)Lb, (size_t)H, st);
+      if (e != cudaSuccess) return (int)e;
+      const int rc = launch_k_outliers(p, /*zero_first=*/0, 1.f, st);
+      if (rc != 0) return rc;
+      accumulate = 1;
+    }
+    const int rc = (rope_half == nullptr)     // exact mode: fp32 ratio form (kvq_kratio.cu); else the fp16-table form
+        ? k_ratio_dispatch(bits, q, cache, scores, score_stride, lut, H, Lmax, Lb, rope, rope_npos, pos_offset, gmax, scale,
+                           accumulate, len_dev, len_add, qtab, t0, run_prep, st)
+        : k_fast_dispatch(bits, q, cache, scores, score_stride, lut, H, Lmax, Lb, rope_half, rope_npos, pos_offset, gmax,
+                          scale, accumulate, len_dev, len_add, qtab, t0, run_prep, st);
+    if (rc != 0) return rc;
+    run_prep = 0;
+    if (Lb != kBlock) break;
+  }
+  return 0;
 }
 
 }  // namespace kvq

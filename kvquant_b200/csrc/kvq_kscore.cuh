@@ -70,10 +70,12 @@ int k_scores3_dispatch(const KParams& p, cudaStream_t st);
 // dense K-score kernel of the fused attend, exact fp32 ratio form (kvq_kratio.cu)
 int k_ratio_dispatch(int bits, const float* q, const int32_t* cache, float* scores, int64_t score_stride, const float* lut,
                      int H, int64_t Lmax, int64_t L, const float* rope, int64_t rope_npos, int pos_offset, float* gmax,
-                     float scale, int accumulate, const int64_t* len_dev, int64_t len_add, void* qtab, cudaStream_t st);
+                     float scale, int accumulate, const int64_t* len_dev, int64_t len_add, void* qtab, int64_t t0,
+                     int run_prep, cudaStream_t st);
 // dense K-score kernel of the fused attend, fp16-table form (kvq_kfast.cu)
 int k_fast_dispatch(int bits, const float* q, const int32_t* cache, float* scores, int64_t score_stride, const float* lut,
                     int H, int64_t Lmax, int64_t L, const void* rope_half, int64_t rope_npos, int pos_offset, float* gmax,
-                    float scale, int accumulate, const int64_t* len_dev, int64_t len_add, void* qtab, cudaStream_t st);
+                    float scale, int accumulate, const int64_t* len_dev, int64_t len_add, void* qtab, int64_t t0,
+                     int run_prep, cudaStream_t st);
 
 }  // namespace kvq

@@ -524,7 +524,7 @@ int v_native_dispatch(int bits, const float* score, int64_t score_stride, const 
 
 int k_scores_fused_fast(int bits, const float* q, const int32_t* cache, float* scores, int64_t score_stride,
                         const float* lut, const float* outliers, const int32_t* outlier_idx, int n_out, int H,
-                        int64_t Lmax, int64_t L, const float* rope, const void* rope_half, int64_t rope_npos,
+                        int64_t Lmax, int64_t L, const float* rope, const void* rope_half, int64_t rope_npos, float theta,
                         int pos_offset, float* gmax, float scale, const int64_t* len_dev, int64_t len_add, void* qtab,
                         cudaStream_t st);
 // KVQ_K_IMPL set (generic / pair / kappa / lds64): round 1's 8-byte-entry kernels serve the exact mode of the fused attend
@@ -623,7 +623,7 @@ static int attend_impl(int bits, const float* q, const int32_t* kcache, const fl
                           rope_cos_sin, rope_npos, theta, pos_offset, gmax, scale, len_dev, len_add, opart, opart_stride, st);
     else
       rc = k_scores_fused_fast(bits, q, kcache, scores, stride, klut, k_outliers, k_outlier_idx, n_out, H, Lmax, L,
-                               rope_cos_sin, rope_half, rope_npos, pos_offset, gmax, scale, len_dev, len_add, qtab, st);
+                               rope_cos_sin, rope_half, rope_npos, theta, pos_offset, gmax, scale, len_dev, len_add, qtab, st);
     if (rc) return rc;
     rc = KVQ_E_UNSUPPORTED;
     if (native_v)
