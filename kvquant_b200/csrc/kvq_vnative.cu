@@ -24,6 +24,11 @@ constexpr int kNThreads = 512;
 constexpr int kNT = 32;          // tokens per stage (128-byte rows, 128B swizzle)
 constexpr int kNMaxStages = 3;   // a 4th stage fits at 3 bits but measured no faster (0.395 vs 0.392 ms attend at 128K)
 constexpr int kNTokPerWarp = kNT / (kNThreads / 32);   // outlier rows handled by one warp per tile (2)
+// row strides of the staged weights (floats).  Lanes of a warp sit in up to 8 different heads (3-bit) and read the SAME
+// token columns: with 32-float rows every head's row starts in bank 0 -- an 8-way conflict on the LDS.128 of w*sf and a
+// ~25-way one on the outlier weight gather (ncu round 2: 6.3 M of 28.9 M shared wavefronts were conflicts at 3 bits).
+constexpr int kNWStride = 33;    // w      : scalar gathers, head h token t -> bank (h + t) % 32
+constexpr int kNWsStride = 36;   // w * sf : 16-byte reads, head h chunk q -> bank group (h + q) % 8
 
 struct VNParams {
   const float* score;        // [H, score_stride] scaled scores
@@ -54,8 +59,8 @@ __host__ __device__ inline VNSmem vn_smem_layout(int rows, int tabn, int H, int 
   s.stage_bytes = (uint32_t)rows * (kNT * 4);
   s.off_tab = s.stage_bytes * n_stages;              // stages first (1024-aligned), then the table
   s.off_w = s.off_tab + (uint32_t)tabn * 256u;
-  s.off_ws = s.off_w + 2u * H * kNT * 4;
-  s.off_oacc = s.off_ws + 2u * H * kNT * 4;
+  s.off_ws = (s.off_w + 2u * H * kNWStride * 4 + 15u) & ~15u;
+  s.off_oacc = s.off_ws + 2u * H * kNWsStride * 4;
   s.off_bar = s.off_oacc;   // (the outlier accumulator lives in the partial-output row in global memory)
   s.total = s.off_bar + 8u * kNMaxStages;
   return s;
@@ -129,8 +134,8 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
   const int rows = p.H * W;
   const VNSmem lay = vn_smem_layout(rows, TABN, p.H, p.n_stages);
   float2* s_tab = reinterpret_cast<float2*>(smem + lay.off_tab);   // [TABN][32 lanes]
-  float* s_w = reinterpret_cast<float*>(smem + lay.off_w);         // [2][H][16]   w = exp(s - max)
-  float* s_ws = reinterpret_cast<float*>(smem + lay.off_ws);       // [2][H][16]   w * sf_t
+  float* s_w = reinterpret_cast<float*>(smem + lay.off_w);         // [2][H][kNWStride]    w = exp(s - max)
+  float* s_ws = reinterpret_cast<float*>(smem + lay.off_ws);       // [2][H][kNWsStride]   w * sf_t
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + lay.off_bar);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -258,7 +263,11 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
       const int e = tid + i * kNThreads;
-      if (e < n_w) { s_w[buf * n_w + e] = wpre[i]; s_ws[buf * n_w + e] = wspre[i]; }
+      if (e < n_w) {
+        const int h = e >> 5, tl = e & 31;
+        s_w[(buf * p.H + h) * kNWStride + tl] = wpre[i];
+        s_ws[(buf * p.H + h) * kNWsStride + tl] = wspre[i];
+      }
     }
   };
   // outliers: O[j] += w[h(j), t] * val(t, j).  Warp w owns tokens {w, w+16} of the tile; lanes walk the row (no
@@ -303,11 +312,11 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
     const int s = it % S;
     mbar_wait(&s_bar[s], (uint32_t)((it / S) & 1));
     const unsigned char* stage = smem + (size_t)s * lay.stage_bytes;
-    const float* wsbuf = s_ws + (it & 1) * n_w;
+    const float* wsbuf = s_ws + (it & 1) * p.H * kNWsStride;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       if (u_on[i]) {
-        const float* wsrow = wsbuf + u_head[i] * kNT;
+        const float* wsrow = wsbuf + u_head[i] * kNWsStride;
         if constexpr (BITS == 3) {
           if (sub == 0) vn_tile_unit<3, 0>(stage, r_off[i], r_swz[i], r_off2[i], r_swz2[i], 0, tab, wsrow, acc[i]);
           else if (sub == 1) vn_tile_unit<3, 1>(stage, r_off[i], r_swz[i], r_off2[i], r_swz2[i], 0, tab, wsrow, acc[i]);
@@ -318,7 +327,7 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
       }
     }
     if (has_out) {
-      const float* wbuf = s_w + (it & 1) * n_w;
+      const float* wbuf = s_w + (it & 1) * p.H * kNWStride;
 #pragma unroll
       for (int j = 0; j < kNTokPerWarp; ++j) {
         const int tl = warp + j * (kNThreads / 32);
@@ -327,7 +336,7 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
           const float v = opre_v[2 * j + r];
           if (v != 0.f) {
             const int idx = opre_i[2 * j + r];
-            red_add_f32(obase + idx, v * wbuf[(idx >> 7) * kNT + tl]);
+            red_add_f32(obase + idx, v * wbuf[(idx >> 7) * kNWStride + tl]);
           }
         }
         for (int k = lane + 64; k < p.n_out; k += 32) {   // n_out > 64: unprefetched tail
@@ -335,7 +344,7 @@ __global__ void __launch_bounds__(kNThreads, 1) v_native_kernel(const __grid_con
           if (t < L_eff) {
             const float v = p.outliers[t * p.n_out + k];
             const int idx = p.outlier_idx[t * p.n_out + k];
-            if (v != 0.f) red_add_f32(obase + idx, v * wbuf[(idx >> 7) * kNT + tl]);
+            if (v != 0.f) red_add_f32(obase + idx, v * wbuf[(idx >> 7) * kNWStride + tl]);
           }
         }
       }
