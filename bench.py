@@ -317,9 +317,11 @@ def main():
     ap.add_argument("--graph", default="dynamic", choices=["dynamic", "static"],
                     help="dynamic: cache length / position live on the device and every replay is the NEXT decode step "
                          "(growing cache); static: every replay re-runs the step at the captured length")
-    ap.add_argument("--sp-exchange", default="nccl", choices=["nccl", "p2p"],
-                    help="sp only: how the per-GPU partial attention results meet -- nccl: all_gather + merge kernel "
-                         "(default, validated); p2p: EXPERIMENTAL peer-memory exchange fused with the merge")
+    ap.add_argument("--sp-exchange", default="p2p", choices=["nccl", "p2p"],
+                    help="sp only: how the per-GPU partial attention results meet -- p2p (default): ONE kernel per layer "
+                         "stores the 16.6 KB partial straight into the peers' IPC-mapped buffers over NVLink, waits for "
+                         "theirs and merges (validated against NCCL at 2/4/8 GPUs, tests/test_zz_p2p_exchange.py); "
+                         "nccl: all_gather + merge kernel")
     ap.add_argument("--torch-profile", default="", help="write a per-kernel table of 3 graph replays to this file (diagnostic)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -397,10 +399,19 @@ def main():
         lo, hi = 0, cfg.n_layers
         stage = kd.DecoderStage(cfg, lo, hi, dev, quantizer, seed=0, with_head=True, sp=(rank, world))
         stage.global_pos = n_sink + L
+        config["sp_exchange"] = "nccl all_gather + merge kernel"
         if args.sp_exchange == "p2p":
             from kvquant_b200.p2p import PeerExchange
-            stage.xchg = PeerExchange(rank, world, cfg.n_heads, dev)
-            config["sp_exchange"] = "p2p (experimental)"
+            try:
+                stage.xchg = PeerExchange(rank, world, cfg.n_heads, dev)
+                config["sp_exchange"] = "peer-memory stores over NVLink fused with the merge (kvq_attend_exchange_merge)"
+            except Exception as e:  # noqa: BLE001  (no peer access / IPC: fall back to the NCCL path on every rank)
+                stage.xchg = None
+                config["sp_exchange"] += " (peer exchange unavailable: %s)" % repr(e)[:80]
+            ok = torch.tensor([1 if stage.xchg is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                stage.xchg = None
     else:
         lo, hi = kd.partition_layers(cfg.n_layers, world, rank)
         stage = kd.DecoderStage(cfg, lo, hi, dev, quantizer, seed=0, with_head=(rank == 0))
@@ -477,6 +488,11 @@ def main():
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    if sp_mode and stage.xchg is not None:
+        bad = torch.tensor([1 if stage.xchg.failed() else 0], device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()):
+            raise SystemExit("peer-memory exchange timed out on some rank: results invalid (rerun with --sp-exchange nccl)")
     ms_step = ms_total / args.steps
     value = 1000.0 / ms_step
     e2e_value = 1000.0 / (ms_e2e / args.steps)

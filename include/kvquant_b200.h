@@ -218,8 +218,8 @@ KVQ_API int kvq_append_v_orig(int32_t* cache, const float* lut_tok, const float*
                       int32_t* out_count, int H, int64_t Lmax, int64_t slot, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * EXPERIMENTAL (not yet validated on a multi-GPU box; the default sequence-sharded path uses NCCL + kvq_attend_merge):
- * exchange of the per-GPU partial attention results over NVLink peer memory, fused with their merge.
+ * Exchange of the per-GPU partial attention results over NVLink peer memory, fused with their merge (sequence-sharded
+ * decode; validated against NCCL all_gather + kvq_attend_merge at 2 / 4 / 8 GPUs, tests/test_zz_p2p_exchange.py).
  *   kvq_p2p_buffer_bytes(world, H)          size of one rank's exchange buffer
  *   kvq_p2p_alloc / kvq_p2p_free            cudaMalloc'ed, zeroed buffer + its 64-byte CUDA IPC handle
  *   kvq_p2p_open / kvq_p2p_close            map a peer's buffer from its handle

@@ -102,7 +102,7 @@ class DecoderStage:
         self.sp = sp
         self.global_pos = None   # sp: absolute position of the new token (set by the driver)
         self.dyn = None          # device-resident length / position counters (enable_device_length)
-        self.xchg = None         # sp: optional kvquant_b200.p2p.PeerExchange (experimental) instead of NCCL all_gather
+        self.xchg = None         # sp: kvquant_b200.p2p.PeerExchange (peer-memory exchange) instead of NCCL all_gather
         gen = torch.Generator(device=self.device)
         gen.manual_seed(seed * 1000 + lo)
         self.layers = [DecoderLayer(cfg, self.device, gen, quantizer, with_sinks=(sp is None or sp[0] == 0))
@@ -211,7 +211,7 @@ class DecoderStage:
                     c.attend_dyn(qh, dyn["len"], 1 if owner else 0, rope_theta=cfg.rope_theta,
                                  out=part[:hid].view(H, HEAD_DIM), lse=part[hid:])
                 o = b["om"]
-                if self.xchg is not None:                         # experimental: peer-memory exchange fused with the merge
+                if self.xchg is not None:                         # peer-memory exchange fused with the merge (one kernel per layer)
                     self.xchg.exchange_merge(part, o)
                 else:
                     dist.all_gather_into_tensor(b["gath"], part)  # H*129 floats per rank over NVLink
