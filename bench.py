@@ -117,7 +117,8 @@ def build_quantizer(cfg_bits, H, device):
 # ------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: CPU port of the path on the host cores, fixed bounded sample, no GPU involved
 # ------------------------------------------------------------------------------------------------------------
-CPU_SAMPLE_TOKENS = 32768      # tokens of ONE layer per timed call (fixed: the same work on every box and every run)
+# tokens of ONE layer per timed call (fixed: the same work on every box and every run; the override is for the tests)
+CPU_SAMPLE_TOKENS = int(os.environ.get("KVQ_CPU_SAMPLE_TOKENS", "32768"))
 
 
 def host_cores():
@@ -338,7 +339,7 @@ def main():
     metric = "decode tokens/sec @ seqlen %dK (LLaMA-%s, bs1)" % (L // 1024, model.upper())
     base = {"metric": metric, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic (random-init fp16 LLaMA-7B weights, synthetic K/V packed by the real prefill packers)"}
+            "data": "synthetic (random-init fp16 LLaMA-%s weights, synthetic K/V packed by the real prefill packers)" % model.upper()}
 
     if args.impl == "reference":
         if rank != 0:
