@@ -396,23 +396,46 @@ def main():
         return 0
 
     # ---------------------------------------------------------------------------------------------------------
+    sp_exchange = None
     if sp_mode:
         lo, hi = 0, cfg.n_layers
         stage = kd.DecoderStage(cfg, lo, hi, dev, quantizer, seed=0, with_head=True, sp=(rank, world))
         stage.global_pos = n_sink + L
-        config["sp_exchange"] = "nccl all_gather + merge kernel"
+        sp_exchange = "nccl all_gather + merge kernel"
         if args.sp_exchange == "p2p":
             from kvquant_b200.p2p import PeerExchange
             try:
                 stage.xchg = PeerExchange(rank, world, cfg.n_heads, dev)
-                config["sp_exchange"] = "peer-memory stores over NVLink fused with the merge (kvq_attend_exchange_merge)"
+                sp_exchange = "peer-memory stores over NVLink fused with the merge (kvq_attend_exchange_merge)"
             except Exception as e:  # noqa: BLE001  (no peer access / IPC: fall back to the NCCL path on every rank)
                 stage.xchg = None
-                config["sp_exchange"] += " (peer exchange unavailable: %s)" % repr(e)[:80]
+                sp_exchange += " (peer exchange unavailable: %s)" % repr(e)[:80]
             ok = torch.tensor([1 if stage.xchg is not None else 0], device=dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if int(ok.item()) == 0:
                 stage.xchg = None
+            else:
+                # self-test on this box before anything is captured: 16 exchanges of random partials against
+                # all_gather + kvq_attend_merge (tests/_p2p_check.py does 200); any rank unhappy -> every rank uses NCCL
+                n = cfg.hidden + cfg.n_heads
+                good = 1
+                for it in range(16):
+                    part = torch.randn(n, device=dev)
+                    gath = torch.empty(world * n, device=dev)
+                    dist.all_gather_into_tensor(gath, part)
+                    want = torch.empty(cfg.hidden, device=dev)
+                    _lib.check(_lib.load().kvq_attend_merge(gath.data_ptr(), world, cfg.n_heads, want.data_ptr(),
+                                                            torch.cuda.current_stream().cuda_stream))
+                    got = torch.empty(cfg.hidden, device=dev)
+                    stage.xchg.exchange_merge(part, got)
+                    torch.cuda.synchronize()
+                    if stage.xchg.failed() or not torch.isfinite(got).all() or (got - want).abs().max().item() > 1e-5 * max(1.0, want.abs().max().item()):
+                        good = 0          # (no early exit: the ranks must stay in lockstep through the collectives)
+                ok = torch.tensor([good], device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if int(ok.item()) == 0:
+                    stage.xchg = None
+                    sp_exchange = "nccl all_gather + merge kernel (peer exchange failed its self-test on this box)"
     else:
         lo, hi = kd.partition_layers(cfg.n_layers, world, rank)
         stage = kd.DecoderStage(cfg, lo, hi, dev, quantizer, seed=0, with_head=(rank == 0))
@@ -570,7 +593,8 @@ def main():
 
     if rank == 0:
         setup = dict(cache_fill_s=round(t_fill, 1), weight_bytes=stage.weight_bytes(),
-                     cache_bytes_per_layer=kd.layer_step_bytes(cfg, L), table_precision=stage.layers[0].cache.precision)
+                     cache_bytes_per_layer=kd.layer_step_bytes(cfg, L), table_precision=stage.layers[0].cache.precision,
+                     sp_exchange=sp_exchange)
         line = dict(base, value=value, ms_per_step=ms_step, config=config, setup=setup, clocks=clocks,
                     e2e={"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": 8,
                          "d2h_bytes_per_step": cfg.vocab * 2},
