@@ -1,4 +1,5 @@
-// kvquant_b200 -- Q.K^T decode matvec of the fused attend, fp16-table form (the default of kvq_attend).
+// kvquant_b200 -- Q.K^T decode matvec of the fused attend, fp16-table form (opt-in: kvq_attend with rope_half != NULL;
+// the default is the exact ratio form, kvq_kratio.cu).
 //
 // Replaces (reference deployment/kvquant/quant_cuda_kernel.cu):
 //   VecQuant{4,3,2}MatMulKernelNUQPerChannelTransposedRopeMHABatchedFusedOpt   3040-3209, 3692-4115, 4747-4996
@@ -7,7 +8,8 @@
 //
 // What bounded the fp32 kernels (kvq_kscore.cu / kvq_k3.cu) was the SM's shared-memory data path: an 8-byte table
 // entry per element costs two 128-byte wavefronts per warp lookup (ncu: 78-86 % busy).  north_star asks for an fp16
-// LUT and a 1e-3 tolerance, so here
+// LUT and a 1e-3 tolerance (measured: within 1e-3 at a few thousand tokens, 1.4e-3 .. 2.2e-3 at 128K -- which is why
+// this form is opt-in), so here
 //   * the premultiplied table T[h][c][code] = half2(LUT*q_c, s_c*LUT*q_{c^64}) is built ONCE per call by a prep
 //     kernel (k_fast_prep_kernel) and bulk-copied into shared memory (cp.async.bulk): one LDS.32 = one wavefront per
 //     warp lookup, and G = 16 (4-bit) / 32 (3-, 2-bit) heads share one CTA, so a token's cos/sin are loaded once per
@@ -15,9 +17,10 @@
 //   * cos/sin come from a half2 copy of the rope table (same reference expressions, rounded once), held in
 //     registers for all 64 pairs of the thread's token; products are exact in fp32 and accumulate in fp32 with the
 //     mixed-precision FMA of sm_100 (fma.rn.f32.f16 -> FHFMA, one issue slot, half-select operands);
-//   * the packed codes reach shared memory by TMA (cp.async.bulk.tensor.2d boxes of [W rows x 128 tokens], four per
-//     head slab) through a 3-6 stage full/empty mbarrier ring filled by a producer warp: 64+ KiB in flight per SM
-//     without spending registers or issue slots on global loads; thread = token, warps drift apart by up to a ring.
+//   * the packed codes reach shared memory by TMA (cp.async.bulk.tensor.2d boxes of [W rows x 64 tokens], four per
+//     head slab) through a 5-8 stage full/empty mbarrier ring filled by a producer warp: 64+ KiB in flight per SM
+//     without spending registers or issue slots on global loads; a warp = 16 tokens x 2 channel halves, warps drift
+//     apart by up to a ring.
 // Per element: 1 PRMT (3-bit: SHF+LOP3) + 1 LDS.32 + 2 FHFMA.
 #include "kvq_kscore.cuh"
 #include <cuda_fp16.h>
