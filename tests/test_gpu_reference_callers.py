@@ -111,6 +111,17 @@ def test_reference_quantk_quantv_run_unmodified_on_the_shim(mods, bits):
     # 3-bit V prefill: the reference kernel indexes the LUT by channel for entries 1..7 (quant_cuda_kernel.cu:2574-2579,
     # a defect our packer does not reproduce) -> compare V codes from the decode-time slots only
     v_lo = T if bits == 3 else 0
+    same_k = (torch.equal(ka.kcache[:, :, :L], kb.kcache[:, :, :L]) and torch.equal(ka.outlier_indices[:L], kb.outlier_indices[:L])
+              and torch.equal(ka.outliers[:L], kb.outliers[:L]))
+    if not same_k:
+        # the decode-time slots never depend on the prefill packer: they must agree in any case
+        assert torch.equal(ka.kcache[:, :, T:L], kb.kcache[:, :, T:L]), "K cache words of the decode steps differ"
+        assert torch.equal(ka.outlier_indices[T:L], kb.outlier_indices[T:L]) and torch.equal(ka.outliers[T:L], kb.outliers[T:L])
+        # prefill slots: is the reference reproducible here?  (its packer races, see above)
+        kb2, _, _, _ = _drive(on_ref.QuantK, on_ref.QuantV, *args)
+        if not (torch.equal(kb.kcache[:, :, :T], kb2.kcache[:, :, :T]) and torch.equal(kb.outliers[:T], kb2.outliers[:T])):
+            pytest.skip("the reference's K prefill packer disagreed with itself on this run (shared-memory race, "
+                        "quant_cuda_kernel.cu:1857-1883); decode-time state verified bit-identical")
     assert torch.equal(ka.kcache[:, :, :L], kb.kcache[:, :, :L]), "K cache words differ"
     assert torch.equal(va.vcache[:, :, v_lo:L], vb.vcache[:, :, v_lo:L]), "V cache words differ"
     assert torch.equal(va.lookup_table[:L], vb.lookup_table[:L]), "per-token V LUT rows differ"
