@@ -34,3 +34,25 @@ def test_c_port_matches_numpy_oracle(bits, sparse):
                         c.k_out.shape[1], 32, c.Lmax, L, 10000.0, 0, _p(out), _p(scratch))
     _, want = O.attend_ideal(c.k_scores(q), c.v_output)
     assert rel_err(out, want)[0] < 1e-4
+
+
+def test_c_port_k_outliers_only_matches_numpy_oracle():
+    """BASELINE configs[4]'s cache form (capped K outliers, dense-only V): the port takes NULL V outlier rows."""
+    import build_oracle_c
+    from _util import quantizer
+    lib = build_oracle_c.load()
+    bits, H, L = 3, 32, 50
+    klut_d, vcent = quantizer(bits)
+    sp = spec()
+    c = O.OracleCache(bits, H, 128, klut_d, vcent, include_sparse=True, sparse_v=False)
+    k, v = sp.k_tokens(L, 51), sp.v_tokens(L, 52)
+    for t in range(L):
+        c.append(k[t], v[t])
+    q = np.ascontiguousarray(O.rope_rotate_q(sp.q_vec(3), L, 10000.0))
+    klut = np.ascontiguousarray(c.klut["lut"])
+    out = np.zeros((H, 128), np.float32)
+    scratch = np.zeros((H, L), np.float32)
+    lib.kvq_port_attend(bits, _p(q), _p(c.kwords), _p(klut), _p(c.k_out), _p(c.k_idx), _p(c.vwords), _p(c.vlut), None, None,
+                        c.k_out.shape[1], H, c.Lmax, L, 10000.0, 0, _p(out), _p(scratch))
+    _, want = O.attend_ideal(c.k_scores(q), c.v_output)
+    assert rel_err(out, want)[0] < 1e-4
