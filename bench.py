@@ -581,8 +581,10 @@ def main():
                 "per_rank": [{"rank": r, "ms_per_launch": float(m), "gbs": b_att / float(m) / 1e6,
                               "frac": b_att / float(m) / 1e6 / peak} for r, m in enumerate(ms_all.tolist())],
                 "attend_share_of_step": ms_att * len(layers) / ms_step}
-        roof["kernel"] = ("kvq_attend (table precision %s) = attend_init + k_fast_prep + [memset + k_outlier_pers] + "
-                          "k_fast (fp32: k_scores / k_scores3) + v_native + attend_combine" % layers[0].cache.precision)
+        prec = layers[0].cache.precision
+        k_names = ("k_ratio_prep", "k_ratio") if prec == "fp32" else ("k_fast_prep", "k_fast")
+        roof["kernel"] = ("kvq_attend (table precision %s) = attend_init + %s + [memset + k_outlier_pers] + %s + v_native + "
+                          "attend_combine" % (prec, k_names[0], k_names[1]))
         if not args.no_anchors:
             roof["reference_cuda"] = reference_cuda_anchor(layers[0].cache, cfg, Lq, n_sink, bits, ms_att, peak)
             roof["north_star_kernel"] = north_star_anchor(dev, cfg, peak)
