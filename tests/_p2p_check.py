@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""torchrun --nproc-per-node N scripts/r2_p2p_check.py : kvq_attend_exchange_merge (peer-memory exchange fused with the
+"""torchrun --nproc-per-node N tests/_p2p_check.py : kvq_attend_exchange_merge (peer-memory exchange fused with the
 merge) against NCCL all_gather + kvq_attend_merge on the same random partial results, many rounds (both buffer parities,
 advancing sequence numbers).  Prints the max difference on rank 0."""
 import os, sys

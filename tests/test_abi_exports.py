@@ -130,3 +130,35 @@ def test_algorithmic_bytes_match_the_survey_figures():
     cfg.include_sparse = False
     assert kd.layer_step_bytes(cfg, 1) == 4160
     assert 2 * n_outliers_each(4096, 0.99) == 42 and 2 * n_outliers_each(5120, 0.99) == 52
+
+
+def test_ctypes_table_matches_the_header_argument_by_argument():
+    """Every prototype of include/kvquant_b200.h against kvquant_b200._lib.SIGNATURES: same number of parameters and the
+    same class (pointer / int / int64_t / float) in each position -- a binding that drifts from the header would pass
+    garbage in registers without any error."""
+    from kvquant_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "kvquant_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", " ", hdr)
+    protos = re.findall(r"KVQ_API\s+([\w\s\*]+?)\b(kvq_\w+)\s*\(([^)]*)\)\s*;", hdr)
+    assert len(protos) == len(_lib.SIGNATURES)
+
+    def klass_c(decl):
+        decl = decl.strip()
+        if "*" in decl:
+            return "ptr"
+        base = " ".join(decl.split()[:-1]) if len(decl.split()) > 1 else decl     # drop the parameter name
+        base = base.replace("const", "").strip()
+        return {"int": "int", "int64_t": "i64", "float": "f32", "uint64_t": "u64", "unsigned long long": "u64"}[base]
+
+    def klass_py(t):
+        return {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int: "int", ctypes.c_int64: "i64",
+                ctypes.c_float: "f32", ctypes.c_uint64: "u64"}[t]
+
+    for ret, name, params in protos:
+        restype, argtypes = _lib.SIGNATURES[name]
+        plist = [p for p in params.split(",") if p.strip() and p.strip() != "void"]
+        got = [klass_c(p) for p in plist]
+        want = [klass_py(t) for t in argtypes]
+        assert got == want, (name, got, want)
+        assert klass_c(ret.strip() + " x") == klass_py(restype), (name, ret)
